@@ -1,0 +1,149 @@
+#!/usr/bin/env python
+"""Generate tests/golden/*.npz by running the REFERENCE'S OWN Python ops on seeded inputs.
+
+Run in the build container only (needs /root/reference):   python oracle/make_golden.py
+The GPU box has no /root/reference; tests there read the committed fixtures.
+
+How each op of the reference is executed (no reference source is copied into this repo):
+  * apply_disparity          -- imported from models/torch_dsnet.py (sys.modules stub for the absent
+                                `spatial_correlation_sampler`), called with tensor_type='torch.FloatTensor'.
+  * matchshifted, disparityregression -- imported from models_psmnet/submodule.py with
+                                torch.Tensor.cuda patched to the identity (they hard-code .cuda()).
+  * concat-volume loop       -- it is inlined in PSMNet.forward (models_psmnet/stackhourglass.py:110-119);
+                                we read exactly those source lines from the reference file at
+                                generation time and exec them against seeded features.
+  * correlation              -- NOT available (third-party, absent): fixtures come from
+                                oracle/torch_ref.corr_ref evaluated in float64 and are labelled
+                                `pinned=False` inside the file.
+Gradients are produced by autograd through the reference's own graph.
+"""
+from __future__ import annotations
+
+import os
+import sys
+import textwrap
+import types
+
+import numpy as np
+import torch
+
+REF = "/root/reference"
+HERE = os.path.dirname(os.path.abspath(__file__))
+OUT = os.path.join(os.path.dirname(HERE), "tests", "golden")
+sys.path.insert(0, os.path.dirname(HERE))
+
+
+def _load_reference():
+    if not os.path.isdir(REF):
+        raise SystemExit("/root/reference not present: fixtures can only be regenerated in the build container")
+    sys.path.insert(0, REF)
+    for name, attrs in {"spatial_correlation_sampler": {"SpatialCorrelationSampler": object},
+                        "efficientnet_pytorch": {"EfficientNet": object}}.items():
+        m = types.ModuleType(name)
+        m.__dict__.update(attrs)
+        sys.modules[name] = m
+    torch.Tensor.cuda = lambda self, *a, **k: self  # the PSMNet ops hard-code .cuda()
+    from models.torch_dsnet import apply_disparity
+    from models_psmnet.submodule import disparityregression, matchshifted
+    return apply_disparity, disparityregression, matchshifted
+
+
+def _reference_volume_loop(ref_fea, tgt_fea, maxdisp):
+    """exec lines 110-119 of the reference's stackhourglass.py (the inlined volume builder)."""
+    from torch.autograd import Variable
+    path = os.path.join(REF, "models_psmnet", "stackhourglass.py")
+    with open(path) as f:
+        lines = f.readlines()
+    src = textwrap.dedent("".join(lines[109:119]))
+    assert "cost = Variable(torch.FloatTensor" in src and "cost.contiguous()" in src, src
+    ns = {"torch": torch, "Variable": Variable, "refimg_fea": ref_fea, "targetimg_fea": tgt_fea,
+          "self": types.SimpleNamespace(maxdisp=maxdisp)}
+    exec(src, ns)
+    return ns["cost"]
+
+
+def main():
+    os.makedirs(OUT, exist_ok=True)
+    apply_disparity, disparityregression, matchshifted = _load_reference()
+    from oracle import torch_ref
+    g = torch.Generator().manual_seed(1234)
+
+    # ---- a4 warp ------------------------------------------------------------------------------
+    N, C, H, W = 2, 3, 5, 16
+    img = torch.randn(N, C, H, W, generator=g).requires_grad_(True)
+    off = (torch.rand(N, 1, H, W, generator=g) * 12.0 - 8.0)
+    off[0, 0, 0, :6] = torch.tensor([-2.5, 0.0, 0.25, 0.5, 5.0, 0.0])
+    off[0, 0, 1, :] = 0.0                      # zero offset: identity except last column = 0
+    off[0, 0, 2, :] = -torch.arange(W).float()  # lands exactly on x = 0 (closed clamp boundary)
+    off[1, 0, 0, :] = float(W)                 # saturates on the right
+    off[1, 0, 1, :] = (W - 1) - torch.arange(W).float()  # lands exactly on x = W-1
+    off.requires_grad_(True)
+    out = apply_disparity(img, off, tensor_type="torch.FloatTensor")
+    gout = torch.randn(out.shape, generator=g)
+    gimg, goff = torch.autograd.grad(out, (img, off), gout)
+    np.savez(os.path.join(OUT, "warp_small.npz"), img=img.detach().numpy(), off=off.detach().numpy(),
+             out=out.detach().contiguous().numpy(), gout=gout.numpy(), gimg=gimg.numpy(), goff=goff.numpy(),
+             out_stride=np.array(out.stride()))
+    # the survey's probe vector
+    img1 = torch.arange(10.0, 16.0).view(1, 1, 1, 6).requires_grad_(True)
+    off1 = torch.tensor([-2.5, 0.0, 0.25, 0.5, 5.0, 0.0]).view(1, 1, 1, 6).requires_grad_(True)
+    out1 = apply_disparity(img1, off1, tensor_type="torch.FloatTensor")
+    gi1, go1 = torch.autograd.grad(out1.sum(), (img1, off1))
+    np.savez(os.path.join(OUT, "warp_probe.npz"), img=img1.detach().numpy(), off=off1.detach().numpy(),
+             out=out1.detach().contiguous().numpy(), gimg=gi1.numpy(), goff=go1.numpy())
+
+    # ---- a2 concat volume ------------------------------------------------------------------------
+    B, C, H, W, maxdisp = 2, 3, 4, 12, 20  # maxdisp//4 = 5 planes
+    ref = torch.randn(B, C, H, W, generator=g).requires_grad_(True)
+    tgt = torch.randn(B, C, H, W, generator=g).requires_grad_(True)
+    cost = _reference_volume_loop(ref, tgt, maxdisp)
+    D = maxdisp // 4
+    assert tuple(cost.shape) == (B, 2 * C, D, H, W)
+    for s in range(D):  # the single-slice module must agree with the loop, bit for bit
+        assert torch.equal(matchshifted()(ref, tgt, s)[:, :, 0], cost[:, :, s])
+    gcost = torch.randn(cost.shape, generator=g)
+    gref, gtgt = torch.autograd.grad(cost, (ref, tgt), gcost)
+    np.savez(os.path.join(OUT, "concat_small.npz"), ref=ref.detach().numpy(), tgt=tgt.detach().numpy(),
+             cost=cost.detach().numpy(), gcost=gcost.numpy(), gref=gref.numpy(), gtgt=gtgt.numpy(),
+             ndisp=np.array(D))
+    ms = matchshifted()(ref, tgt, 3)
+    np.savez(os.path.join(OUT, "matchshifted_small.npz"), left=ref.detach().numpy(), right=tgt.detach().numpy(),
+             shift=np.array(3), out=ms.detach().numpy())
+
+    # ---- a3 disparityregression / soft-argmin ------------------------------------------------------
+    B, D, H, W = 2, 12, 3, 8
+    logits = (4.0 * torch.randn(B, D, H, W, generator=g)).requires_grad_(True)
+    logits.data[0, :, 0, 0] = -30.0
+    logits.data[0, 7, 0, 0] = 30.0            # one-hot -> soft-argmin = 7
+    p = torch.nn.functional.softmax(logits, dim=1)
+    out = disparityregression(D)(p)
+    gout = torch.randn(out.shape, generator=g)
+    (glog,) = torch.autograd.grad(out, logits, gout)
+    x = torch.rand(B, D, H, W, generator=g).requires_grad_(True)
+    outx = disparityregression(D)(x)
+    (gx,) = torch.autograd.grad(outx, x, gout)
+    np.savez(os.path.join(OUT, "softargmin_small.npz"), cost=logits.detach().numpy(), out=out.detach().numpy(),
+             gout=gout.numpy(), gcost=glog.numpy(), x=x.detach().numpy(), dispreg_out=outx.detach().numpy(),
+             gx=gx.numpy())
+
+    # ---- a1 correlation (UNPINNED: float64 restatement) --------------------------------------------
+    B, C, H, W = 2, 5, 4, 16
+    a = torch.randn(B, C, H, W, generator=g)
+    b = torch.randn(B, C, H, W, generator=g)
+    cases = {"p1x8": ((1, 8), 1), "p1x7": ((1, 7), 1), "p3x5": ((3, 5), 1), "p1x5d2": ((1, 5), 2)}
+    blob = {"in1": a.numpy(), "in2": b.numpy(), "pinned": np.array(False)}
+    for name, (patch, dil) in cases.items():
+        a64 = a.double().requires_grad_(True)
+        b64 = b.double().requires_grad_(True)
+        o = torch_ref.corr_ref(a64, b64, patch, dil)
+        go = torch.randn(o.shape, generator=g, dtype=torch.float64)
+        g1, g2 = torch.autograd.grad(o, (a64, b64), go)
+        blob.update({f"{name}_out": o.detach().numpy(), f"{name}_gout": go.numpy(),
+                     f"{name}_g1": g1.numpy(), f"{name}_g2": g2.numpy(),
+                     f"{name}_patch": np.array(patch), f"{name}_dil": np.array(dil)})
+    np.savez(os.path.join(OUT, "corr_small_unpinned.npz"), **blob)
+    print("wrote", sorted(os.listdir(OUT)))
+
+
+if __name__ == "__main__":
+    main()
