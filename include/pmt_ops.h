@@ -1,0 +1,134 @@
+/*
+ * pmt_ops.h -- C ABI of libpmt_ops.so: B200 (sm_100a) kernels for the stereo cost-volume hot path of
+ * cuevhv/PMT_learning_for_semantic_segmentation_and_disparity.
+ *
+ * Conventions (all entry points)
+ *   - plain pointers and sizes only; no torch types.  Every pointer is a DEVICE pointer to a dense
+ *     row-major fp32 tensor unless its name ends in `_host`.
+ *   - the caller owns every buffer; the library never allocates, frees or retains device memory
+ *     (the `_host` convenience entry points allocate and free their own scratch inside the call).
+ *   - `stream` is a cudaStream_t passed as void*; kernels are only enqueued, never synchronised
+ *     (the `_host` entry points synchronise before returning because they hand back host data).
+ *   - return value 0 = success; non-zero = error, message via pmt_last_error() (thread-local).
+ *   - there is no CPU fallback anywhere in this library.
+ *
+ * Each entry point cites the reference interface it replaces (file:line in the reference repo).
+ */
+#ifndef PMT_OPS_H_
+#define PMT_OPS_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PMT_OK 0
+#define PMT_ERR_INVALID 1   /* bad shape / argument */
+#define PMT_ERR_CUDA 2      /* CUDA runtime / driver error */
+#define PMT_ERR_UNSUPPORTED 3
+
+/* library version (major*10000 + minor*100 + patch) and last error of the calling thread */
+int pmt_version(void);
+const char* pmt_last_error(void);
+/* 1 if device `dev` can run this library (compute capability 10.x), else 0 */
+int pmt_device_supported(int dev);
+
+/* ---------------------------------------------------------------------------------------------
+ * a1. spatial_correlation_sampler backend (third-party pybind module
+ *     `spatial_correlation_sampler_backend.forward/backward`), as constructed at
+ *     models/dsnet_t2.py:129-133,425,847-851,1078-1087; models/dsnet_t2_warp.py:197,506,615,742,877;
+ *     models/torch_dsnet.py:133-138; models_deeplab_mod/net.py:99-103  (kernel_size=1, stride=1,
+ *     padding=0, dilation=1 at every call site).
+ *
+ *   out[n,ph,pw,h,w] = sum_c in1[n,c,h,w] * in2[n,c,h+sh,w+sw]   (terms outside the image skipped)
+ *   sh = (ph-(patchH-1)/2)*dilpH, sw = (pw-(patchW-1)/2)*dilpW;  out is (B,patchH,patchW,H,W).
+ *
+ * pmt_corr1d_*: the 1 x P horizontal patch (the hot path; `-corrType 1dcorr`).  Dispatches to the
+ *   TMA-tiled register-blocked kernels when W%4==0, pointers are 16-byte aligned, dilp==1 and
+ *   P<=193; otherwise to the generic CUDA kernels below.  Backward is a deterministic gather.
+ * pmt_corr_*: any (patchH, patchW, dilation_patch) -- generic CUDA kernels (2-D 17x17 patches of
+ *   `-corrType 2dcorr`, the (1,21) dilation_patch=4 sampler of torch_dsnet.py:133-138).
+ * ------------------------------------------------------------------------------------------- */
+int pmt_corr1d_fwd_f32(const float* in1, const float* in2, float* out, int B, int C, int H, int W,
+                       int P, int dilp, void* stream);
+int pmt_corr1d_bwd_f32(const float* in1, const float* in2, const float* gout, float* gin1,
+                       float* gin2, int B, int C, int H, int W, int P, int dilp, void* stream);
+int pmt_corr_fwd_f32(const float* in1, const float* in2, float* out, int B, int C, int H, int W,
+                     int patchH, int patchW, int dilpH, int dilpW, void* stream);
+int pmt_corr_bwd_f32(const float* in1, const float* in2, const float* gout, float* gin1,
+                     float* gin2, int B, int C, int H, int W, int patchH, int patchW, int dilpH,
+                     int dilpW, void* stream);
+/* which kernel family pmt_corr1d_* would use for this problem: 1 = tiled fast path, 0 = generic */
+int pmt_corr1d_uses_fast_path(const void* in1, const void* in2, const void* out_or_gout, int C,
+                              int H, int W, int P, int dilp);
+
+/* ---------------------------------------------------------------------------------------------
+ * a2. PSMNet concat cost volume -- replaces the slice-assign loop of
+ *     models_psmnet/stackhourglass.py:110-119 (and matchshifted, models_psmnet/submodule.py:45-54,
+ *     which is the single-plane case D=1 with plane index `first_disp`).
+ *   cost[b, c,   i, h, w] = ref[b,c,h,w]          if w >= d else 0     d = first_disp + i
+ *   cost[b, C+c, i, h, w] = tgt[b,c,h,w-d]        if w >= d else 0     i in [0, D)
+ *   Every element of `cost` (B,2C,D,H,W) is written (no reliance on pre-zeroed memory).
+ *   Backward: gref[b,c,h,w] = sum_i gcost[b,c,i,h,w][w>=d];  gtgt[b,c,h,w'] = sum_i gcost[b,C+c,i,h,w'+d]
+ * ------------------------------------------------------------------------------------------- */
+int pmt_concat_volume_fwd_f32(const float* ref, const float* tgt, float* cost, int B, int C, int D,
+                              int H, int W, int first_disp, void* stream);
+int pmt_concat_volume_bwd_f32(const float* gcost, float* gref, float* gtgt, int B, int C, int D,
+                              int H, int W, int first_disp, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * a3. disparityregression (models_psmnet/submodule.py:56-64) and the fused
+ *     F.softmax(dim=1) + disparityregression pair (models_psmnet/stackhourglass.py:142-155).
+ *   dispreg:    out[b,h,w] = sum_d x[b,d,h,w] * d ;            gx[b,d,h,w] = d * gout[b,h,w]
+ *   softargmin: out = sum_d d * softmax(cost)[d]  (single pass, online softmax);
+ *               `lse` (B,H,W) receives max + log(sum exp) for the backward (may be NULL).
+ *               gcost[b,d,h,w] = gout * p_d * (d - out),  p_d = exp(cost - lse)
+ * ------------------------------------------------------------------------------------------- */
+int pmt_dispreg_fwd_f32(const float* x, float* out, int B, int D, int H, int W, void* stream);
+int pmt_dispreg_bwd_f32(const float* gout, float* gx, int B, int D, int H, int W, void* stream);
+int pmt_softargmin_fwd_f32(const float* cost, float* out, float* lse, int B, int D, int H, int W,
+                           void* stream);
+int pmt_softargmin_bwd_f32(const float* cost, const float* out, const float* lse, const float* gout,
+                           float* gcost, int B, int D, int H, int W, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * a4. apply_disparity(input_images, x_offset, wrap_mode='edge') -- models/torch_dsnet.py:10-86.
+ *   x = clamp(w + off[n,0,h,w], 0, W-1); x0 = floor(x); x1 = min(x0+1, W-1)
+ *   out[n,c,h,w] = (x1-x)*img[n,c,h,x0] + (x-x0)*img[n,c,h,x1]       (fp32 steps as the reference)
+ *   `out` is written in the reference's storage order [C][N][H][W] when out_cnhw != 0 (the
+ *   reference returns that buffer permuted to (N,C,H,W), torch_dsnet.py:84), else [N][C][H][W].
+ *   The flat gather index is formed in fp32 exactly as torch_dsnet.py:59-70 does (only matters when
+ *   N*H*W >= 2^24).  Backward: gimg must be ZEROED by the caller (scatter target, fp32 atomics);
+ *   goff[n,0,h,w] = sum_c gout*(img[x1]-img[x0]) where 0 <= w+off <= W-1, else 0.
+ *   `gout` uses the same storage order flag as `out`.
+ * ------------------------------------------------------------------------------------------- */
+int pmt_warp1d_fwd_f32(const float* img, const float* off, float* out, int N, int C, int H, int W,
+                       int out_cnhw, void* stream);
+int pmt_warp1d_bwd_f32(const float* img, const float* off, const float* gout, float* gimg,
+                       float* goff, int N, int C, int H, int W, int gout_cnhw, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Host-buffer entry point for the headline workload (what a non-PyTorch caller of the reference's
+ * sampler backend would bind): forward + backward of the 1 x P correlation on HOST tensors.
+ * Copies in (in1,in2,gout), runs both kernels, copies out (out,gin1,gin2), batch item by batch
+ * item on two streams so copies overlap compute, then synchronises.  Host buffers should be
+ * pinned for full PCIe rate.  Returns 0 on success.
+ * ------------------------------------------------------------------------------------------- */
+int pmt_corr1d_fwd_bwd_host_f32(const float* in1_host, const float* in2_host, const float* gout_host,
+                                float* out_host, float* gin1_host, float* gin2_host, int B, int C,
+                                int H, int W, int P, int dilp);
+
+/* ---------------------------------------------------------------------------------------------
+ * Measurement helpers used by bench.py for the roofline denominators that MEASURED_PEAKS.json does
+ * not carry.  pmt_probe_fp32_fma: runs a register-resident FFMA loop on every SM and returns the
+ * achieved TFLOP/s in *tflops (timed with CUDA events on `stream`).  pmt_probe_copy: device copy
+ * of `bytes` bytes src->dst with a float4 grid-stride kernel, returns GB/s (read+write).
+ * ------------------------------------------------------------------------------------------- */
+int pmt_probe_fp32_fma(int iters, double* tflops, void* stream);
+int pmt_probe_copy(const void* src, void* dst, int64_t bytes, double* gbps, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PMT_OPS_H_ */

@@ -85,6 +85,10 @@ void pmt_oracle_corr_fwd(const float* in1, const float* in2, float* out, int B, 
   corr_out_size(iH, iW, &p, &oH, &oW);
   const int radH = (p.patchH - 1) / 2, radW = (p.patchW - 1) / 2;
   const int64_t plane = (int64_t)iH * iW;
+  /* Upstream accumulates `*dst += v1*v2` with the channel loop outermost inside correlate_patch.
+   * We keep exactly that per-element order (c, then i, then j) but walk a whole output row per
+   * (c,i,j) so the memory accesses are contiguous; every output element sees the same sequence of
+   * fp32 additions as in the upstream loop nest. */
 #pragma omp parallel for collapse(2) schedule(static)
   for (int n = 0; n < B; ++n) {
     for (int ph = 0; ph < p.patchH; ++ph) {
@@ -93,21 +97,23 @@ void pmt_oracle_corr_fwd(const float* in1, const float* in2, float* out, int B, 
       for (int pw = 0; pw < p.patchW; ++pw) {
         const int sh = (ph - radH) * p.dilpH, sw = (pw - radW) * p.dilpW;
         for (int h = 0; h < oH; ++h) {
-          for (int w = 0; w < oW; ++w) {
-            const int u = -p.padH + h * p.dH, v = -p.padW + w * p.dW;
-            float acc = 0.0f; /* output is zero-initialised, then += in channel order */
-            for (int c = 0; c < C; ++c) {
-              for (int i = 0; i < p.kH; ++i) {
-                const int i1 = u + i * p.dilH, i2 = i1 + sh;
-                if (i1 < 0 || i1 >= iH || i2 < 0 || i2 >= iH) continue;
-                for (int j = 0; j < p.kW; ++j) {
-                  const int j1 = v + j * p.dilW, j2 = j1 + sw;
+          float* orow = out + ((((int64_t)n * p.patchH + ph) * p.patchW + pw) * oH + h) * (int64_t)oW;
+          for (int w = 0; w < oW; ++w) orow[w] = 0.0f; /* output is zero-initialised */
+          const int u = -p.padH + h * p.dH;
+          for (int c = 0; c < C; ++c) {
+            for (int i = 0; i < p.kH; ++i) {
+              const int i1 = u + i * p.dilH, i2 = i1 + sh;
+              if (i1 < 0 || i1 >= iH || i2 < 0 || i2 >= iH) continue;
+              const float* arow = a + c * plane + (int64_t)i1 * iW;
+              const float* brow = b + c * plane + (int64_t)i2 * iW;
+              for (int j = 0; j < p.kW; ++j) {
+                for (int w = 0; w < oW; ++w) {
+                  const int j1 = -p.padW + w * p.dW + j * p.dilW, j2 = j1 + sw;
                   if (j1 < 0 || j1 >= iW || j2 < 0 || j2 >= iW) continue;
-                  acc += a[c * plane + (int64_t)i1 * iW + j1] * b[c * plane + (int64_t)i2 * iW + j2];
+                  orow[w] += arow[j1] * brow[j2];
                 }
               }
             }
-            out[((((int64_t)n * p.patchH + ph) * p.patchW + pw) * oH + h) * oW + w] = acc;
           }
         }
       }

@@ -1,0 +1,14 @@
+"""B200-native stereo cost-volume hot path (drop-in ops for
+cuevhv/PMT_learning_for_semantic_segmentation_and_disparity).
+
+Everything here dispatches to hand-written sm_100a kernels in libpmt_ops.so through the C ABI declared in
+include/pmt_ops.h.  There is no CPU, PyTorch-eager or Triton fallback: if the library is missing the ops raise.
+"""
+from ._lib import PmtOpsError, load as load_library  # noqa: F401
+from .correlation import (SpatialCorrelationSampler, SpatialCorrelationSamplerFunction,  # noqa: F401
+                          spatial_correlation_sample)
+from .psmnet import build_concat_volume, disparityregression, matchshifted, softargmin  # noqa: F401
+from .warp import apply_disparity  # noqa: F401
+from .compat import install_reference_shims  # noqa: F401
+
+__version__ = "0.1.0"

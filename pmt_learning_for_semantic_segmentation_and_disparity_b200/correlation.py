@@ -1,0 +1,99 @@
+"""Drop-in for the third-party ``spatial_correlation_sampler`` package on B200.
+
+Mirrors the surface the reference constructs (models/dsnet_t2.py:129-133,425,847-851,1078-1087;
+models/dsnet_t2_warp.py:197,506,615,742,877; models/torch_dsnet.py:133-138;
+models_deeplab_mod/net.py:99-103): ``SpatialCorrelationSampler(kernel_size, patch_size, stride, padding,
+dilation, dilation_patch)(input1, input2) -> (B, pH, pW, H, W)``, the functional
+``spatial_correlation_sample`` and the autograd ``SpatialCorrelationSamplerFunction`` whose backward
+returns ``(grad_input1, grad_input2, None x 6)``.
+
+Every call site of the reference uses kernel_size=1, stride=1, padding=0, dilation=1; that is what the
+CUDA kernels implement (any patch_size, any dilation_patch).  Other values raise NotImplementedError --
+there is no silent fallback.
+"""
+from __future__ import annotations
+
+import torch
+from torch import nn
+from torch.autograd import Function
+from torch.autograd.function import once_differentiable
+
+from . import _util as U
+
+
+def _check_supported(kernel_size, stride, padding, dilation):
+    kH, kW = U.pair(kernel_size, "kernel_size")
+    dH, dW = U.pair(stride, "stride")
+    padH, padW = U.pair(padding, "padding")
+    dilH, dilW = U.pair(dilation, "dilation")
+    if (kH, kW) != (1, 1) or (dH, dW) != (1, 1) or (padH, padW) != (0, 0):
+        raise NotImplementedError(
+            "B200 correlation implements kernel_size=1, stride=1, padding=0 (every reference call site); got "
+            f"kernel_size={kernel_size}, stride={stride}, padding={padding}")
+    del dilH, dilW  # dilation is irrelevant for a 1x1 kernel
+
+
+class SpatialCorrelationSamplerFunction(Function):
+    @staticmethod
+    def forward(ctx, input1, input2, kernel_size=1, patch_size=1, stride=1, padding=0, dilation=1,
+                dilation_patch=1):
+        _check_supported(kernel_size, stride, padding, dilation)
+        pH, pW = U.pair(patch_size, "patch_size")
+        dpH, dpW = U.pair(dilation_patch, "dilation_patch")
+        if pH < 1 or pW < 1 or dpH < 1 or dpW < 1:
+            raise ValueError("patch_size and dilation_patch must be >= 1")
+        in1 = U.require_cuda_f32(input1, "input1")
+        in2 = U.require_cuda_f32(input2, "input2")
+        if in1.dim() != 4 or in1.shape != in2.shape:
+            raise ValueError(f"input1/input2 must be 4-D (B,C,H,W) of equal shape, got {tuple(input1.shape)} and "
+                             f"{tuple(input2.shape)}")
+        dev = U.same_device(in1, in2)
+        B, C, H, W = in1.shape
+        ctx.save_for_backward(in1, in2)
+        ctx.patch = (pH, pW, dpH, dpW)
+        out = torch.empty((B, pH, pW, H, W), device=dev, dtype=torch.float32)
+        U.call("pmt_corr_fwd_f32", dev, U.ptr(in1), U.ptr(in2), U.ptr(out), B, C, H, W, pH, pW, dpH, dpW)
+        return out
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, grad_output):
+        in1, in2 = ctx.saved_tensors
+        pH, pW, dpH, dpW = ctx.patch
+        B, C, H, W = in1.shape
+        g = U.require_cuda_f32(grad_output, "grad_output")
+        g1 = torch.empty_like(in1)
+        g2 = torch.empty_like(in2)
+        U.call("pmt_corr_bwd_f32", in1.device, U.ptr(in1), U.ptr(in2), U.ptr(g), U.ptr(g1), U.ptr(g2), B, C, H, W,
+               pH, pW, dpH, dpW)
+        return g1, g2, None, None, None, None, None, None
+
+
+def spatial_correlation_sample(input1, input2, kernel_size=1, patch_size=1, stride=1, padding=0, dilation=1,
+                               dilation_patch=1):
+    """Functional form; returns (B, pH, pW, H, W), un-normalised (callers divide by C themselves for the
+    2-D patch, models/dsnet_t2.py:223,884)."""
+    return SpatialCorrelationSamplerFunction.apply(input1, input2, kernel_size, patch_size, stride, padding,
+                                                   dilation, dilation_patch)
+
+
+class SpatialCorrelationSampler(nn.Module):
+    """Parameter-free module, same constructor keywords as the upstream class."""
+
+    def __init__(self, kernel_size=1, patch_size=1, stride=1, padding=0, dilation=1, dilation_patch=1):
+        super().__init__()
+        self.kernel_size = kernel_size
+        self.patch_size = patch_size
+        self.stride = stride
+        self.padding = padding
+        self.dilation = dilation
+        self.dilation_patch = dilation_patch
+
+    def forward(self, input1, input2):
+        return SpatialCorrelationSamplerFunction.apply(input1, input2, self.kernel_size, self.patch_size,
+                                                       self.stride, self.padding, self.dilation,
+                                                       self.dilation_patch)
+
+    def extra_repr(self):
+        return (f"kernel_size={self.kernel_size}, patch_size={self.patch_size}, stride={self.stride}, "
+                f"padding={self.padding}, dilation={self.dilation}, dilation_patch={self.dilation_patch}")

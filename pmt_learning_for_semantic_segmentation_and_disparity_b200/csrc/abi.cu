@@ -1,0 +1,354 @@
+// abi.cu -- extern "C" surface of libpmt_ops.so (see include/pmt_ops.h), argument validation,
+// dispatch between the tiled fast paths and the generic kernels, TMA descriptor construction and
+// the measurement probes.  No CPU fallback exists: unsupported requests return an error.
+#include <stdarg.h>
+#include <string.h>
+
+#include "common.cuh"
+
+namespace pmt {
+
+// launchers implemented in the other translation units
+int launch_corr_generic_fwd(const float*, const float*, float*, int, int, int, int, int, int, int, int,
+                            cudaStream_t);
+int launch_corr_generic_bwd(const float*, const float*, const float*, float*, float*, int, int, int,
+                            int, int, int, int, int, cudaStream_t);
+bool corr1d_fwd_fast_ok(const void*, const void*, int W, int P, int dilp);
+int launch_corr1d_fwd_tiled(const float*, const float*, float*, int, int, int, int, int, cudaStream_t);
+bool corr1d_bwd_fast_ok(const void*, const void*, const void*, int C, int W, int P, int dilp);
+int launch_corr1d_bwd_tiled(const float*, const float*, const float*, float*, float*, int, int, int,
+                            int, int, cudaStream_t);
+int launch_concat_fwd(const float*, const float*, float*, int, int, int, int, int, int, cudaStream_t);
+int launch_concat_bwd(const float*, float*, float*, int, int, int, int, int, int, cudaStream_t);
+int launch_softargmin_fwd(const float*, float*, float*, int, int, int, int, cudaStream_t);
+int launch_softargmin_bwd(const float*, const float*, const float*, const float*, float*, int, int,
+                          int, int, cudaStream_t);
+int launch_dispreg_fwd(const float*, float*, int, int, int, int, cudaStream_t);
+int launch_dispreg_bwd(const float*, float*, int, int, int, int, cudaStream_t);
+int launch_warp_fwd(const float*, const float*, float*, int, int, int, int, int, cudaStream_t);
+int launch_warp_bwd(const float*, const float*, const float*, float*, float*, int, int, int, int, int,
+                    cudaStream_t);
+
+// ---- error text ---------------------------------------------------------------------------------
+static thread_local char g_err[512] = "";
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+const char* get_error() { return g_err; }
+
+int sm_count() {
+  static int cached[64] = {0};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 148;
+  if (cached[dev] == 0) {
+    int n = 0;
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+    cached[dev] = n;
+  }
+  return cached[dev];
+}
+
+// ---- TMA descriptor construction (driver entry point fetched through the runtime: no -lcuda) ----
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,
+                                  CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
+                                  CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_tiled_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (fn == nullptr) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
+int make_tmap_nchw(CUtensorMap* map, const float* base, int B, int C, int H, int W, int box_w,
+                   int box_c) {
+  EncodeTiledFn enc = encode_tiled_fn();
+  if (enc == nullptr) {
+    set_error("cuTensorMapEncodeTiled not available from the driver");
+    return PMT_ERR_CUDA;
+  }
+  const cuuint64_t dims[4] = {(cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)C, (cuuint64_t)B};
+  const cuuint64_t strides[3] = {(cuuint64_t)W * 4, (cuuint64_t)W * H * 4, (cuuint64_t)W * H * C * 4};
+  const cuuint32_t box[4] = {(cuuint32_t)box_w, 1u, (cuuint32_t)box_c, 1u};
+  const cuuint32_t estr[4] = {1u, 1u, 1u, 1u};
+  const CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(base), dims, strides,
+                         box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                         CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled failed (CUresult %d) for dims (%d,%d,%d,%d) box (%d,1,%d,1)", (int)r,
+              W, H, C, B, box_w, box_c);
+    return PMT_ERR_CUDA;
+  }
+  return PMT_OK;
+}
+
+// ---- probes -------------------------------------------------------------------------------------
+namespace {
+
+__global__ void __launch_bounds__(256) fp32_fma_probe_kernel(float* sink, int iters, float a, float b) {
+  // 16 independent accumulators per thread, 2 multiplier registers: the register operand pattern
+  // of an outer-product micro-kernel (acc = fma(x_i, y_j, acc)).
+  float acc[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) acc[i] = (float)(threadIdx.x + i);
+  float x0 = a, x1 = a + 1.f, x2 = a + 2.f, x3 = a + 3.f, y0 = b, y1 = b + 1.f, y2 = b + 2.f, y3 = b + 3.f;
+  for (int it = 0; it < iters; ++it) {
+#pragma unroll
+    for (int r = 0; r < 8; ++r) {
+      acc[0] = fmaf(x0, y0, acc[0]);   acc[1] = fmaf(x0, y1, acc[1]);
+      acc[2] = fmaf(x0, y2, acc[2]);   acc[3] = fmaf(x0, y3, acc[3]);
+      acc[4] = fmaf(x1, y0, acc[4]);   acc[5] = fmaf(x1, y1, acc[5]);
+      acc[6] = fmaf(x1, y2, acc[6]);   acc[7] = fmaf(x1, y3, acc[7]);
+      acc[8] = fmaf(x2, y0, acc[8]);   acc[9] = fmaf(x2, y1, acc[9]);
+      acc[10] = fmaf(x2, y2, acc[10]); acc[11] = fmaf(x2, y3, acc[11]);
+      acc[12] = fmaf(x3, y0, acc[12]); acc[13] = fmaf(x3, y1, acc[13]);
+      acc[14] = fmaf(x3, y2, acc[14]); acc[15] = fmaf(x3, y3, acc[15]);
+    }
+  }
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < 16; ++i) s += acc[i];
+  if (s == 123.456f) sink[0] = s;  // never true in practice; keeps the loop alive
+}
+
+__global__ void __launch_bounds__(256) copy_probe_kernel(const float4* __restrict__ src,
+                                                         float4* __restrict__ dst, int64_t n4) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4;
+       i += (int64_t)gridDim.x * blockDim.x)
+    __stcs(dst + i, __ldcs(src + i));
+}
+
+}  // namespace
+}  // namespace pmt
+
+using namespace pmt;
+
+extern "C" {
+
+int pmt_version(void) { return 100; /* 0.1.0 */ }
+const char* pmt_last_error(void) { return get_error(); }
+
+int pmt_device_supported(int dev) {
+  int major = 0;
+  if (cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev) != cudaSuccess) return 0;
+  return major == 10 ? 1 : 0;
+}
+
+static int check_corr_args(const void* a, const void* b, const void* c, int B, int C, int H, int W,
+                           int pH, int pW, int dpH, int dpW) {
+  PMT_CHECK_ARG(a && b && c, "correlation: null pointer");
+  PMT_CHECK_ARG(B >= 0 && C >= 0 && H >= 0 && W >= 0, "correlation: negative dimension");
+  PMT_CHECK_ARG(pH >= 1 && pW >= 1 && dpH >= 1 && dpW >= 1, "correlation: patch/dilation_patch must be >= 1");
+  return PMT_OK;
+}
+
+int pmt_corr1d_uses_fast_path(const void* in1, const void* in2, const void* third, int C, int H, int W,
+                              int P, int dilp) {
+  (void)H;
+  return (corr1d_fwd_fast_ok(in1, in2, W, P, dilp) && corr1d_bwd_fast_ok(in1, in2, third, C, W, P, dilp)) ? 1 : 0;
+}
+
+int pmt_corr1d_fwd_f32(const float* in1, const float* in2, float* out, int B, int C, int H, int W, int P,
+                       int dilp, void* stream) {
+  if (int e = check_corr_args(in1, in2, out, B, C, H, W, 1, P, 1, dilp)) return e;
+  if ((int64_t)B * H * W == 0) return PMT_OK;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (C > 0 && corr1d_fwd_fast_ok(in1, in2, W, P, dilp))
+    return launch_corr1d_fwd_tiled(in1, in2, out, B, C, H, W, P, st);
+  return launch_corr_generic_fwd(in1, in2, out, B, C, H, W, 1, P, 1, dilp, st);
+}
+
+int pmt_corr1d_bwd_f32(const float* in1, const float* in2, const float* gout, float* gin1, float* gin2,
+                       int B, int C, int H, int W, int P, int dilp, void* stream) {
+  if (int e = check_corr_args(in1, in2, gout, B, C, H, W, 1, P, 1, dilp)) return e;
+  PMT_CHECK_ARG(gin1 && gin2, "correlation backward: null gradient pointer");
+  if ((int64_t)B * C * H * W == 0) return PMT_OK;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (corr1d_bwd_fast_ok(in1, in2, gout, C, W, P, dilp) && aligned16(gin1) && aligned16(gin2))
+    return launch_corr1d_bwd_tiled(in1, in2, gout, gin1, gin2, B, C, H, W, P, st);
+  return launch_corr_generic_bwd(in1, in2, gout, gin1, gin2, B, C, H, W, 1, P, 1, dilp, st);
+}
+
+int pmt_corr_fwd_f32(const float* in1, const float* in2, float* out, int B, int C, int H, int W, int pH,
+                     int pW, int dpH, int dpW, void* stream) {
+  if (int e = check_corr_args(in1, in2, out, B, C, H, W, pH, pW, dpH, dpW)) return e;
+  if (pH == 1) return pmt_corr1d_fwd_f32(in1, in2, out, B, C, H, W, pW, dpW, stream);
+  return launch_corr_generic_fwd(in1, in2, out, B, C, H, W, pH, pW, dpH, dpW, static_cast<cudaStream_t>(stream));
+}
+
+int pmt_corr_bwd_f32(const float* in1, const float* in2, const float* gout, float* gin1, float* gin2,
+                     int B, int C, int H, int W, int pH, int pW, int dpH, int dpW, void* stream) {
+  if (int e = check_corr_args(in1, in2, gout, B, C, H, W, pH, pW, dpH, dpW)) return e;
+  PMT_CHECK_ARG(gin1 && gin2, "correlation backward: null gradient pointer");
+  if (pH == 1) return pmt_corr1d_bwd_f32(in1, in2, gout, gin1, gin2, B, C, H, W, pW, dpW, stream);
+  return launch_corr_generic_bwd(in1, in2, gout, gin1, gin2, B, C, H, W, pH, pW, dpH, dpW,
+                                 static_cast<cudaStream_t>(stream));
+}
+
+int pmt_concat_volume_fwd_f32(const float* ref, const float* tgt, float* cost, int B, int C, int D, int H,
+                              int W, int first_disp, void* stream) {
+  PMT_CHECK_ARG(ref && tgt && cost, "concat volume: null pointer");
+  PMT_CHECK_ARG(B >= 0 && C >= 0 && D >= 0 && H >= 0 && W >= 0 && first_disp >= 0, "concat volume: negative dimension");
+  return launch_concat_fwd(ref, tgt, cost, B, C, D, H, W, first_disp, static_cast<cudaStream_t>(stream));
+}
+
+int pmt_concat_volume_bwd_f32(const float* gcost, float* gref, float* gtgt, int B, int C, int D, int H,
+                              int W, int first_disp, void* stream) {
+  PMT_CHECK_ARG(gcost && gref && gtgt, "concat volume backward: null pointer");
+  PMT_CHECK_ARG(B >= 0 && C >= 0 && D >= 0 && H >= 0 && W >= 0 && first_disp >= 0, "concat volume: negative dimension");
+  return launch_concat_bwd(gcost, gref, gtgt, B, C, D, H, W, first_disp, static_cast<cudaStream_t>(stream));
+}
+
+int pmt_dispreg_fwd_f32(const float* x, float* out, int B, int D, int H, int W, void* stream) {
+  PMT_CHECK_ARG(x && out, "disparityregression: null pointer");
+  PMT_CHECK_ARG(B >= 0 && D >= 0 && H >= 0 && W >= 0, "disparityregression: negative dimension");
+  return launch_dispreg_fwd(x, out, B, D, H, W, static_cast<cudaStream_t>(stream));
+}
+
+int pmt_dispreg_bwd_f32(const float* gout, float* gx, int B, int D, int H, int W, void* stream) {
+  PMT_CHECK_ARG(gout && gx, "disparityregression backward: null pointer");
+  PMT_CHECK_ARG(B >= 0 && D >= 0 && H >= 0 && W >= 0, "disparityregression: negative dimension");
+  return launch_dispreg_bwd(gout, gx, B, D, H, W, static_cast<cudaStream_t>(stream));
+}
+
+int pmt_softargmin_fwd_f32(const float* cost, float* out, float* lse, int B, int D, int H, int W,
+                           void* stream) {
+  PMT_CHECK_ARG(cost && out, "softargmin: null pointer");
+  PMT_CHECK_ARG(B >= 0 && D >= 1 && H >= 0 && W >= 0, "softargmin: bad dimension");
+  return launch_softargmin_fwd(cost, out, lse, B, D, H, W, static_cast<cudaStream_t>(stream));
+}
+
+int pmt_softargmin_bwd_f32(const float* cost, const float* out, const float* lse, const float* gout,
+                           float* gcost, int B, int D, int H, int W, void* stream) {
+  PMT_CHECK_ARG(cost && out && lse && gout && gcost, "softargmin backward: null pointer");
+  PMT_CHECK_ARG(B >= 0 && D >= 1 && H >= 0 && W >= 0, "softargmin: bad dimension");
+  return launch_softargmin_bwd(cost, out, lse, gout, gcost, B, D, H, W, static_cast<cudaStream_t>(stream));
+}
+
+int pmt_warp1d_fwd_f32(const float* img, const float* off, float* out, int N, int C, int H, int W,
+                       int out_cnhw, void* stream) {
+  PMT_CHECK_ARG(img && off && out, "warp: null pointer");
+  PMT_CHECK_ARG(N >= 0 && C >= 0 && H >= 0 && W >= 0, "warp: negative dimension");
+  return launch_warp_fwd(img, off, out, N, C, H, W, out_cnhw, static_cast<cudaStream_t>(stream));
+}
+
+int pmt_warp1d_bwd_f32(const float* img, const float* off, const float* gout, float* gimg, float* goff,
+                       int N, int C, int H, int W, int gout_cnhw, void* stream) {
+  PMT_CHECK_ARG(img && off && gout, "warp backward: null pointer");
+  PMT_CHECK_ARG(gimg || goff, "warp backward: nothing to compute");
+  PMT_CHECK_ARG(N >= 0 && C >= 0 && H >= 0 && W >= 0, "warp: negative dimension");
+  return launch_warp_bwd(img, off, gout, gimg, goff, N, C, H, W, gout_cnhw, static_cast<cudaStream_t>(stream));
+}
+
+// Host-buffer forward+backward of the 1 x P correlation, one batch item per pipeline slot.
+int pmt_corr1d_fwd_bwd_host_f32(const float* in1_h, const float* in2_h, const float* gout_h, float* out_h,
+                                float* gin1_h, float* gin2_h, int B, int C, int H, int W, int P, int dilp) {
+  PMT_CHECK_ARG(in1_h && in2_h && gout_h && out_h && gin1_h && gin2_h, "host corr: null pointer");
+  PMT_CHECK_ARG(B >= 0 && C >= 1 && H >= 1 && W >= 1 && P >= 1 && dilp >= 1, "host corr: bad dimension");
+  const size_t fe = (size_t)C * H * W, oe = (size_t)P * H * W;
+  constexpr int kSlots = 2;
+  cudaStream_t st[kSlots] = {nullptr, nullptr};
+  float* buf[kSlots] = {nullptr, nullptr};
+  int rc = PMT_OK;
+  auto fail = [&](cudaError_t e, const char* what) {
+    set_error("host corr: %s failed: %s", what, cudaGetErrorString(e));
+    rc = PMT_ERR_CUDA;
+  };
+  const size_t slot_elems = 4 * fe + 2 * oe;  // in1,in2,gin1,gin2 | gout,out
+  for (int s = 0; s < kSlots && rc == PMT_OK; ++s) {
+    cudaError_t e = cudaStreamCreateWithFlags(&st[s], cudaStreamNonBlocking);
+    if (e != cudaSuccess) { fail(e, "cudaStreamCreate"); break; }
+    e = cudaMalloc(&buf[s], slot_elems * sizeof(float));
+    if (e != cudaSuccess) { fail(e, "cudaMalloc"); break; }
+  }
+  for (int n = 0; n < B && rc == PMT_OK; ++n) {
+    const int s = n % kSlots;
+    float *d1 = buf[s], *d2 = d1 + fe, *g1 = d2 + fe, *g2 = g1 + fe, *dg = g2 + fe, *dout = dg + oe;
+    cudaError_t e;
+    if ((e = cudaMemcpyAsync(d1, in1_h + n * fe, fe * 4, cudaMemcpyHostToDevice, st[s])) != cudaSuccess) { fail(e, "H2D in1"); break; }
+    if ((e = cudaMemcpyAsync(d2, in2_h + n * fe, fe * 4, cudaMemcpyHostToDevice, st[s])) != cudaSuccess) { fail(e, "H2D in2"); break; }
+    if ((e = cudaMemcpyAsync(dg, gout_h + n * oe, oe * 4, cudaMemcpyHostToDevice, st[s])) != cudaSuccess) { fail(e, "H2D gout"); break; }
+    if ((rc = pmt_corr1d_fwd_f32(d1, d2, dout, 1, C, H, W, P, dilp, st[s])) != PMT_OK) break;
+    if ((rc = pmt_corr1d_bwd_f32(d1, d2, dg, g1, g2, 1, C, H, W, P, dilp, st[s])) != PMT_OK) break;
+    if ((e = cudaMemcpyAsync(out_h + n * oe, dout, oe * 4, cudaMemcpyDeviceToHost, st[s])) != cudaSuccess) { fail(e, "D2H out"); break; }
+    if ((e = cudaMemcpyAsync(gin1_h + n * fe, g1, fe * 4, cudaMemcpyDeviceToHost, st[s])) != cudaSuccess) { fail(e, "D2H gin1"); break; }
+    if ((e = cudaMemcpyAsync(gin2_h + n * fe, g2, fe * 4, cudaMemcpyDeviceToHost, st[s])) != cudaSuccess) { fail(e, "D2H gin2"); break; }
+  }
+  for (int s = 0; s < kSlots; ++s) {
+    if (st[s]) {
+      cudaError_t e = cudaStreamSynchronize(st[s]);
+      if (e != cudaSuccess && rc == PMT_OK) fail(e, "cudaStreamSynchronize");
+      cudaStreamDestroy(st[s]);
+    }
+    if (buf[s]) cudaFree(buf[s]);
+  }
+  return rc;
+}
+
+int pmt_probe_fp32_fma(int iters, double* tflops, void* stream) {
+  PMT_CHECK_ARG(iters > 0 && tflops, "fp32 probe: bad argument");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  float* sink = nullptr;
+  PMT_CUDA_OK(cudaMalloc(&sink, sizeof(float)));
+  const int blocks = sm_count() * 8;
+  cudaEvent_t e0, e1;
+  PMT_CUDA_OK(cudaEventCreate(&e0));
+  PMT_CUDA_OK(cudaEventCreate(&e1));
+  fp32_fma_probe_kernel<<<blocks, 256, 0, st>>>(sink, iters / 8 + 1, 1.0001f, 0.9999f);  // warm-up
+  float best_ms = 1e30f;
+  for (int rep = 0; rep < 3; ++rep) {
+    PMT_CUDA_OK(cudaEventRecord(e0, st));
+    fp32_fma_probe_kernel<<<blocks, 256, 0, st>>>(sink, iters, 1.0001f, 0.9999f);
+    PMT_CUDA_OK(cudaEventRecord(e1, st));
+    PMT_CUDA_OK(cudaEventSynchronize(e1));
+    float ms = 0.f;
+    PMT_CUDA_OK(cudaEventElapsedTime(&ms, e0, e1));
+    if (ms < best_ms) best_ms = ms;
+  }
+  PMT_LAUNCH_OK("fp32_fma_probe_kernel");
+  const double flops = (double)blocks * 256.0 * (double)iters * 8.0 * 16.0 * 2.0;
+  *tflops = flops / (best_ms * 1e-3) * 1e-12;
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  cudaFree(sink);
+  return PMT_OK;
+}
+
+int pmt_probe_copy(const void* src, void* dst, int64_t bytes, double* gbps, void* stream) {
+  PMT_CHECK_ARG(src && dst && gbps && bytes >= 16 && bytes % 16 == 0, "copy probe: bad argument");
+  PMT_CHECK_ARG(aligned16(src) && aligned16(dst), "copy probe: pointers must be 16-byte aligned");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int64_t n4 = bytes / 16;
+  const int blocks = sm_count() * 16;
+  cudaEvent_t e0, e1;
+  PMT_CUDA_OK(cudaEventCreate(&e0));
+  PMT_CUDA_OK(cudaEventCreate(&e1));
+  copy_probe_kernel<<<blocks, 256, 0, st>>>((const float4*)src, (float4*)dst, n4);
+  float best_ms = 1e30f;
+  for (int rep = 0; rep < 5; ++rep) {
+    PMT_CUDA_OK(cudaEventRecord(e0, st));
+    copy_probe_kernel<<<blocks, 256, 0, st>>>((const float4*)src, (float4*)dst, n4);
+    PMT_CUDA_OK(cudaEventRecord(e1, st));
+    PMT_CUDA_OK(cudaEventSynchronize(e1));
+    float ms = 0.f;
+    PMT_CUDA_OK(cudaEventElapsedTime(&ms, e0, e1));
+    if (ms < best_ms) best_ms = ms;
+  }
+  PMT_LAUNCH_OK("copy_probe_kernel");
+  *gbps = 2.0 * (double)bytes / (best_ms * 1e-3) * 1e-9;
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  return PMT_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,359 @@
+// psmnet_ops.cu -- PSMNet concat cost volume, disparityregression and fused soft-argmin.
+//   concat volume : models_psmnet/stackhourglass.py:110-119, matchshifted submodule.py:45-54
+//   dispreg       : models_psmnet/submodule.py:56-64
+//   soft-argmin   : F.softmax(dim=1) + disparityregression, stackhourglass.py:142-155
+// All four are HBM-bound streaming kernels: every input element is read once and every output
+// element written once with 128-bit accesses; grids are sized in multiples of the SM count.
+#include "common.cuh"
+
+namespace pmt {
+namespace {
+
+// ---------------------------------------------------------------------------------------------
+// concat volume forward: one CTA walks (b, c2, h) source rows; the source row is staged once in
+// shared memory and re-emitted D times (shifted for the target half), so global reads are 1/D of
+// the writes and every write is a full 16-byte streaming store.
+// ---------------------------------------------------------------------------------------------
+template <bool kVec>
+__global__ void __launch_bounds__(128) concat_fwd_kernel(const float* __restrict__ ref,
+                                                         const float* __restrict__ tgt,
+                                                         float* __restrict__ cost, int B, int C, int D,
+                                                         int H, int W, int d0) {
+  extern __shared__ float srow[];
+  const int64_t rows = (int64_t)B * 2 * C * H;
+  for (int64_t r = blockIdx.x; r < rows; r += gridDim.x) {
+    const int h = (int)(r % H);
+    const int c2 = (int)((r / H) % (2 * C));
+    const int b = (int)(r / ((int64_t)H * 2 * C));
+    const bool is_tgt = c2 >= C;
+    const float* src = (is_tgt ? tgt : ref) + (((int64_t)b * C + (is_tgt ? c2 - C : c2)) * H + h) * (int64_t)W;
+    __syncthreads();  // previous row fully consumed
+    if (kVec) {
+      for (int w = threadIdx.x * 4; w < W; w += blockDim.x * 4)
+        *reinterpret_cast<float4*>(srow + w) = __ldg(reinterpret_cast<const float4*>(src + w));
+    } else {
+      for (int w = threadIdx.x; w < W; w += blockDim.x) srow[w] = __ldg(src + w);
+    }
+    __syncthreads();
+    float* dst0 = cost + ((((int64_t)b * 2 * C + c2) * D) * H + h) * (int64_t)W;
+    const int64_t dstride = (int64_t)H * W;
+    if (kVec) {
+      const int nv = W >> 2;
+      for (int e = threadIdx.x; e < D * nv; e += blockDim.x) {
+        const int i = e / nv, w = (e - i * nv) * 4;
+        const int d = d0 + i;
+        const int sh = is_tgt ? d : 0;
+        float4 v;
+        v.x = (w + 0 >= d) ? srow[w + 0 - sh] : 0.f;
+        v.y = (w + 1 >= d) ? srow[w + 1 - sh] : 0.f;
+        v.z = (w + 2 >= d) ? srow[w + 2 - sh] : 0.f;
+        v.w = (w + 3 >= d) ? srow[w + 3 - sh] : 0.f;
+        st_cs4(dst0 + i * dstride + w, v);
+      }
+    } else {
+      for (int e = threadIdx.x; e < D * W; e += blockDim.x) {
+        const int i = e / W, w = e - i * W;
+        const int d = d0 + i;
+        dst0[i * dstride + w] = (w >= d) ? srow[w - (is_tgt ? d : 0)] : 0.f;
+      }
+    }
+  }
+}
+
+// concat volume backward: deterministic gather; one thread per (b,c2,h,w) sums its D planes in
+// descending plane order (the order autograd accumulates the reference's slice assignments).
+__global__ void __launch_bounds__(256) concat_bwd_kernel(const float* __restrict__ gcost,
+                                                         float* __restrict__ gref,
+                                                         float* __restrict__ gtgt, int B, int C, int D,
+                                                         int H, int W, int d0, int64_t total) {
+  const int64_t dstride = (int64_t)H * W;
+  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (int64_t)gridDim.x * blockDim.x) {
+    const int w = (int)(idx % W);
+    int64_t t = idx / W;
+    const int h = (int)(t % H);
+    t /= H;
+    const int c2 = (int)(t % (2 * C));
+    const int b = (int)(t / (2 * C));
+    const bool is_tgt = c2 >= C;
+    const float* g = gcost + ((((int64_t)b * 2 * C + c2) * D) * H + h) * (int64_t)W;
+    float acc = 0.f;
+    if (!is_tgt) {
+#pragma unroll 8
+      for (int i = D - 1; i >= 0; --i)
+        if (w >= d0 + i) acc += __ldg(g + i * dstride + w);
+      gref[(((int64_t)b * C + c2) * H + h) * (int64_t)W + w] = acc;
+    } else {
+#pragma unroll 8
+      for (int i = D - 1; i >= 0; --i)
+        if (w + d0 + i < W) acc += __ldg(g + i * dstride + w + d0 + i);
+      gtgt[(((int64_t)b * C + (c2 - C)) * H + h) * (int64_t)W + w] = acc;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// soft-argmin / disparityregression.  kV pixels per thread (4 with 128-bit accesses when H*W%4==0),
+// planes walked with stride H*W; 8 planes are loaded before use so each thread keeps 8 independent
+// 16-byte loads in flight.
+// ---------------------------------------------------------------------------------------------
+template <int kV>
+struct Vec;
+template <>
+struct Vec<4> {
+  using T = float4;
+};
+template <>
+struct Vec<1> {
+  using T = float;
+};
+
+template <int kV>
+__device__ __forceinline__ void load_vec(const float* p, float (&v)[kV]) {
+  if constexpr (kV == 4) {
+    const float4 t = __ldcs(reinterpret_cast<const float4*>(p));
+    v[0] = t.x, v[1] = t.y, v[2] = t.z, v[3] = t.w;
+  } else {
+    v[0] = __ldcs(p);
+  }
+}
+template <int kV>
+__device__ __forceinline__ void store_vec(float* p, const float (&v)[kV]) {
+  if constexpr (kV == 4) {
+    st_cs4(p, make_float4(v[0], v[1], v[2], v[3]));
+  } else {
+    st_cs(p, v[0]);
+  }
+}
+
+constexpr float kLog2e = 1.4426950408889634f;
+constexpr float kLn2 = 0.6931471805599453f;
+constexpr int kDU = 8;  // planes per unrolled batch
+
+template <int kV>
+__global__ void __launch_bounds__(256) softargmin_fwd_kernel(const float* __restrict__ cost,
+                                                             float* __restrict__ out,
+                                                             float* __restrict__ lse, int D,
+                                                             int64_t plane, int64_t ngroups) {
+  const int64_t gpp = plane / kV;  // pixel groups per batch item
+  for (int64_t gidx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; gidx < ngroups;
+       gidx += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t b = gidx / gpp, k = (gidx % gpp) * kV;
+    const float* base = cost + b * D * plane + k;
+    float m[kV], s[kV], t[kV];
+#pragma unroll
+    for (int v = 0; v < kV; ++v) m[v] = -INFINITY, s[v] = 0.f, t[v] = 0.f;
+    for (int d0 = 0; d0 < D; d0 += kDU) {
+      float x[kDU][kV];
+#pragma unroll
+      for (int j = 0; j < kDU; ++j) {
+        if (d0 + j < D) {
+          load_vec<kV>(base + (int64_t)(d0 + j) * plane, x[j]);
+        } else {
+#pragma unroll
+          for (int v = 0; v < kV; ++v) x[j][v] = -INFINITY;
+        }
+      }
+#pragma unroll
+      for (int v = 0; v < kV; ++v) {
+        float bm = x[0][v];
+#pragma unroll
+        for (int j = 1; j < kDU; ++j) bm = fmaxf(bm, x[j][v]);
+        const float mn = fmaxf(m[v], bm * kLog2e);
+        const float sc = exp2f(m[v] - mn);  // 0 on the first batch (m = -inf)
+        float ss = s[v] * sc, tt = t[v] * sc;
+#pragma unroll
+        for (int j = 0; j < kDU; ++j) {
+          const float e = exp2f(fmaf(x[j][v], kLog2e, -mn));  // exp(x - max); 0 for padded planes
+          ss += e;
+          tt = fmaf(e, (float)(d0 + j), tt);
+        }
+        m[v] = mn, s[v] = ss, t[v] = tt;
+      }
+    }
+    float o[kV], l[kV];
+#pragma unroll
+    for (int v = 0; v < kV; ++v) {
+      o[v] = t[v] / s[v];
+      l[v] = (m[v] + log2f(s[v])) * kLn2;
+    }
+    store_vec<kV>(out + b * plane + k, o);
+    if (lse != nullptr) store_vec<kV>(lse + b * plane + k, l);
+  }
+}
+
+template <int kV>
+__global__ void __launch_bounds__(256) softargmin_bwd_kernel(const float* __restrict__ cost,
+                                                             const float* __restrict__ out,
+                                                             const float* __restrict__ lse,
+                                                             const float* __restrict__ gout,
+                                                             float* __restrict__ gcost, int D,
+                                                             int64_t plane, int64_t ngroups) {
+  const int64_t gpp = plane / kV;
+  for (int64_t gidx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; gidx < ngroups;
+       gidx += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t b = gidx / gpp, k = (gidx % gpp) * kV;
+    float o[kV], l[kV], g[kV];
+    load_vec<kV>(out + b * plane + k, o);
+    load_vec<kV>(lse + b * plane + k, l);
+    load_vec<kV>(gout + b * plane + k, g);
+#pragma unroll
+    for (int v = 0; v < kV; ++v) l[v] *= kLog2e;
+    const float* cbase = cost + b * D * plane + k;
+    float* gbase = gcost + b * D * plane + k;
+    for (int d0 = 0; d0 < D; d0 += kDU) {
+      float x[kDU][kV];
+#pragma unroll
+      for (int j = 0; j < kDU; ++j)
+        if (d0 + j < D) load_vec<kV>(cbase + (int64_t)(d0 + j) * plane, x[j]);
+#pragma unroll
+      for (int j = 0; j < kDU; ++j) {
+        if (d0 + j < D) {
+          float r[kV];
+#pragma unroll
+          for (int v = 0; v < kV; ++v) {
+            const float p = exp2f(fmaf(x[j][v], kLog2e, -l[v]));
+            r[v] = g[v] * p * ((float)(d0 + j) - o[v]);
+          }
+          store_vec<kV>(gbase + (int64_t)(d0 + j) * plane, r);
+        }
+      }
+    }
+  }
+}
+
+template <int kV>
+__global__ void __launch_bounds__(256) dispreg_fwd_kernel(const float* __restrict__ x,
+                                                          float* __restrict__ out, int D,
+                                                          int64_t plane, int64_t ngroups) {
+  const int64_t gpp = plane / kV;
+  for (int64_t gidx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; gidx < ngroups;
+       gidx += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t b = gidx / gpp, k = (gidx % gpp) * kV;
+    const float* base = x + b * D * plane + k;
+    float acc[kV];
+#pragma unroll
+    for (int v = 0; v < kV; ++v) acc[v] = 0.f;
+    for (int d0 = 0; d0 < D; d0 += kDU) {
+      float xv[kDU][kV];
+#pragma unroll
+      for (int j = 0; j < kDU; ++j) {
+        if (d0 + j < D) {
+          load_vec<kV>(base + (int64_t)(d0 + j) * plane, xv[j]);
+        } else {
+#pragma unroll
+          for (int v = 0; v < kV; ++v) xv[j][v] = 0.f;
+        }
+      }
+      // the reference multiplies then sums (x*disp).sum(1): keep the products un-fused, in d order
+#pragma unroll
+      for (int j = 0; j < kDU; ++j)
+#pragma unroll
+        for (int v = 0; v < kV; ++v) acc[v] = __fadd_rn(acc[v], __fmul_rn(xv[j][v], (float)(d0 + j)));
+    }
+    store_vec<kV>(out + b * plane + k, acc);
+  }
+}
+
+template <int kV>
+__global__ void __launch_bounds__(256) dispreg_bwd_kernel(const float* __restrict__ gout,
+                                                          float* __restrict__ gx, int D,
+                                                          int64_t plane, int64_t ngroups) {
+  const int64_t gpp = plane / kV;
+  for (int64_t gidx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; gidx < ngroups;
+       gidx += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t b = gidx / gpp, k = (gidx % gpp) * kV;
+    float g[kV];
+    load_vec<kV>(gout + b * plane + k, g);
+    float* base = gx + b * D * plane + k;
+    for (int d = 0; d < D; ++d) {
+      float r[kV];
+#pragma unroll
+      for (int v = 0; v < kV; ++v) r[v] = (float)d * g[v];
+      store_vec<kV>(base + (int64_t)d * plane, r);
+    }
+  }
+}
+
+int stream_grid(int64_t nthreads) {
+  const int64_t blocks = ceil_div64(nthreads, 256);
+  const int64_t cap = (int64_t)sm_count() * 8;  // 8 x 256 threads = full residency per SM
+  return (int)(blocks < cap ? blocks : cap);
+}
+
+}  // namespace
+
+int launch_concat_fwd(const float* ref, const float* tgt, float* cost, int B, int C, int D, int H,
+                      int W, int d0, cudaStream_t st) {
+  const int64_t rows = (int64_t)B * 2 * C * H;
+  if (rows == 0 || D == 0 || W == 0) return PMT_OK;
+  const int64_t cap = (int64_t)sm_count() * 16;
+  const int grid = (int)(rows < cap ? rows : cap);
+  const size_t smem = (size_t)round_up(W, 4) * sizeof(float);
+  PMT_CHECK_ARG(smem <= 48 * 1024, "concat volume: W=%d too wide for the row stage", W);
+  const bool vec = (W % 4 == 0) && aligned16(ref) && aligned16(tgt) && aligned16(cost);
+  if (vec)
+    concat_fwd_kernel<true><<<grid, 128, smem, st>>>(ref, tgt, cost, B, C, D, H, W, d0);
+  else
+    concat_fwd_kernel<false><<<grid, 128, smem, st>>>(ref, tgt, cost, B, C, D, H, W, d0);
+  PMT_LAUNCH_OK("concat_fwd_kernel");
+  return PMT_OK;
+}
+
+int launch_concat_bwd(const float* gcost, float* gref, float* gtgt, int B, int C, int D, int H, int W,
+                      int d0, cudaStream_t st) {
+  const int64_t total = (int64_t)B * 2 * C * H * W;
+  if (total == 0) return PMT_OK;
+  concat_bwd_kernel<<<stream_grid(total), 256, 0, st>>>(gcost, gref, gtgt, B, C, D, H, W, d0, total);
+  PMT_LAUNCH_OK("concat_bwd_kernel");
+  return PMT_OK;
+}
+
+#define PMT_DISPATCH_VEC(kernel, vec_ok, total_pixels, ...)                                   \
+  do {                                                                                        \
+    if (vec_ok) {                                                                             \
+      const int64_t ng = (total_pixels) / 4;                                                  \
+      kernel<4><<<stream_grid(ng), 256, 0, st>>>(__VA_ARGS__, ng);                            \
+    } else {                                                                                  \
+      const int64_t ng = (total_pixels);                                                      \
+      kernel<1><<<stream_grid(ng), 256, 0, st>>>(__VA_ARGS__, ng);                            \
+    }                                                                                         \
+    PMT_LAUNCH_OK(#kernel);                                                                   \
+  } while (0)
+
+int launch_softargmin_fwd(const float* cost, float* out, float* lse, int B, int D, int H, int W,
+                          cudaStream_t st) {
+  const int64_t plane = (int64_t)H * W;
+  if (B * plane == 0) return PMT_OK;
+  const bool vec = plane % 4 == 0 && aligned16(cost) && aligned16(out) && (lse == nullptr || aligned16(lse));
+  PMT_DISPATCH_VEC(softargmin_fwd_kernel, vec, B * plane, cost, out, lse, D, plane);
+  return PMT_OK;
+}
+
+int launch_softargmin_bwd(const float* cost, const float* out, const float* lse, const float* gout,
+                          float* gcost, int B, int D, int H, int W, cudaStream_t st) {
+  const int64_t plane = (int64_t)H * W;
+  if (B * plane == 0) return PMT_OK;
+  const bool vec = plane % 4 == 0 && aligned16(cost) && aligned16(out) && aligned16(lse) &&
+                   aligned16(gout) && aligned16(gcost);
+  PMT_DISPATCH_VEC(softargmin_bwd_kernel, vec, B * plane, cost, out, lse, gout, gcost, D, plane);
+  return PMT_OK;
+}
+
+int launch_dispreg_fwd(const float* x, float* out, int B, int D, int H, int W, cudaStream_t st) {
+  const int64_t plane = (int64_t)H * W;
+  if (B * plane == 0) return PMT_OK;
+  const bool vec = plane % 4 == 0 && aligned16(x) && aligned16(out);
+  PMT_DISPATCH_VEC(dispreg_fwd_kernel, vec, B * plane, x, out, D, plane);
+  return PMT_OK;
+}
+
+int launch_dispreg_bwd(const float* gout, float* gx, int B, int D, int H, int W, cudaStream_t st) {
+  const int64_t plane = (int64_t)H * W;
+  if (B * plane == 0) return PMT_OK;
+  const bool vec = plane % 4 == 0 && aligned16(gout) && aligned16(gx);
+  PMT_DISPATCH_VEC(dispreg_bwd_kernel, vec, B * plane, gout, gx, D, plane);
+  return PMT_OK;
+}
+
+}  // namespace pmt

@@ -1,0 +1,125 @@
+"""PSMNet hot-path ops on B200: concat cost volume, disparityregression, fused soft-argmin.
+
+Reference surfaces kept: ``disparityregression(maxdisp)(x)`` and ``matchshifted()(left, right, shift)`` of
+models_psmnet/submodule.py:45-64; ``build_concat_volume(ref, tgt, ndisp)`` replaces the slice-assign loop of
+models_psmnet/stackhourglass.py:110-119; ``softargmin(cost)`` replaces the ``F.softmax(cost, dim=1)`` +
+``disparityregression`` pair of stackhourglass.py:142-155.
+"""
+from __future__ import annotations
+
+import torch
+from torch import nn
+from torch.autograd import Function
+from torch.autograd.function import once_differentiable
+
+from . import _util as U
+
+
+class _ConcatVolume(Function):
+    @staticmethod
+    def forward(ctx, ref, tgt, ndisp, first_disp):
+        ref = U.require_cuda_f32(ref, "ref")
+        tgt = U.require_cuda_f32(tgt, "tgt")
+        if ref.dim() != 4 or ref.shape != tgt.shape:
+            raise ValueError(f"ref/tgt must be 4-D (B,C,H,W) of equal shape, got {tuple(ref.shape)}, {tuple(tgt.shape)}")
+        dev = U.same_device(ref, tgt)
+        B, C, H, W = ref.shape
+        ctx.dims = (B, C, int(ndisp), H, W, int(first_disp))
+        cost = torch.empty((B, 2 * C, int(ndisp), H, W), device=dev, dtype=torch.float32)
+        U.call("pmt_concat_volume_fwd_f32", dev, U.ptr(ref), U.ptr(tgt), U.ptr(cost), B, C, int(ndisp), H, W,
+               int(first_disp))
+        return cost
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, gcost):
+        B, C, D, H, W, d0 = ctx.dims
+        g = U.require_cuda_f32(gcost, "grad_cost")
+        gref = torch.empty((B, C, H, W), device=g.device, dtype=torch.float32)
+        gtgt = torch.empty_like(gref)
+        U.call("pmt_concat_volume_bwd_f32", g.device, U.ptr(g), U.ptr(gref), U.ptr(gtgt), B, C, D, H, W, d0)
+        return gref, gtgt, None, None
+
+
+def build_concat_volume(ref: torch.Tensor, tgt: torch.Tensor, ndisp: int) -> torch.Tensor:
+    """(B,C,H,W) x 2 -> contiguous (B,2C,ndisp,H,W); ndisp = maxdisp//4 in PSMNet. Bit-exact vs the loop."""
+    if int(ndisp) < 0:
+        raise ValueError("ndisp must be >= 0")
+    return _ConcatVolume.apply(ref, tgt, int(ndisp), 0)
+
+
+class matchshifted(nn.Module):
+    """models_psmnet/submodule.py:45-54 -- one shifted left||right slice, (B,2C,1,H,W)."""
+
+    def forward(self, left, right, shift):
+        shift = int(shift)
+        if shift < 0 or shift > left.size(3):
+            raise ValueError(f"shift {shift} outside [0, width]")
+        return _ConcatVolume.apply(left, right, 1, shift)
+
+
+class _DispReg(Function):
+    @staticmethod
+    def forward(ctx, x):
+        x = U.require_cuda_f32(x, "x")
+        B, D, H, W = x.shape
+        ctx.dims = (B, D, H, W)
+        out = torch.empty((B, H, W), device=x.device, dtype=torch.float32)
+        U.call("pmt_dispreg_fwd_f32", x.device, U.ptr(x), U.ptr(out), B, D, H, W)
+        return out
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, gout):
+        B, D, H, W = ctx.dims
+        g = U.require_cuda_f32(gout, "grad_output")
+        gx = torch.empty((B, D, H, W), device=g.device, dtype=torch.float32)
+        U.call("pmt_dispreg_bwd_f32", g.device, U.ptr(g), U.ptr(gx), B, D, H, W)
+        return gx
+
+
+class disparityregression(nn.Module):
+    """models_psmnet/submodule.py:56-64: out[b,h,w] = sum_d x[b,d,h,w]*d over an already soft-maxed x."""
+
+    def __init__(self, maxdisp):
+        super().__init__()
+        self.maxdisp = int(maxdisp)
+
+    def forward(self, x):
+        if x.dim() != 4:
+            raise ValueError(f"expected (B,D,H,W), got {tuple(x.shape)}")
+        if x.size(1) != self.maxdisp:
+            # the reference multiplies by a (B,maxdisp,H,W) ramp, which fails to broadcast the same way
+            raise RuntimeError(f"The size of tensor a ({x.size(1)}) must match the size of tensor b "
+                               f"({self.maxdisp}) at non-singleton dimension 1")
+        return _DispReg.apply(x)
+
+
+class _SoftArgmin(Function):
+    @staticmethod
+    def forward(ctx, cost):
+        cost = U.require_cuda_f32(cost, "cost")
+        B, D, H, W = cost.shape
+        out = torch.empty((B, H, W), device=cost.device, dtype=torch.float32)
+        lse = torch.empty_like(out)
+        U.call("pmt_softargmin_fwd_f32", cost.device, U.ptr(cost), U.ptr(out), U.ptr(lse), B, D, H, W)
+        ctx.save_for_backward(cost, out, lse)
+        return out
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, gout):
+        cost, out, lse = ctx.saved_tensors
+        B, D, H, W = cost.shape
+        g = U.require_cuda_f32(gout, "grad_output")
+        gcost = torch.empty_like(cost)
+        U.call("pmt_softargmin_bwd_f32", cost.device, U.ptr(cost), U.ptr(out), U.ptr(lse), U.ptr(g), U.ptr(gcost),
+               B, D, H, W)
+        return gcost
+
+
+def softargmin(cost: torch.Tensor) -> torch.Tensor:
+    """Fused softmax(dim=1) + disparity expectation: (B,D,H,W) -> (B,H,W), one pass over `cost`."""
+    if cost.dim() != 4 or cost.size(1) < 1:
+        raise ValueError(f"expected (B,D,H,W) with D>=1, got {tuple(cost.shape)}")
+    return _SoftArgmin.apply(cost)

@@ -1,0 +1,89 @@
+"""CPU-side checks: the C-ABI library loads without a GPU and exports every symbol include/pmt_ops.h declares;
+the host shims validate arguments like the reference surface; nothing in the product package imports the oracle."""
+import ctypes
+import os
+import re
+import sys
+
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+PKG = os.path.join(ROOT, "pmt_learning_for_semantic_segmentation_and_disparity_b200")
+
+
+@pytest.fixture(scope="module")
+def built():
+    import __graft_entry__ as ge
+    ge.build()
+    import pmt_learning_for_semantic_segmentation_and_disparity_b200 as m
+    return m
+
+
+def declared_symbols():
+    with open(os.path.join(ROOT, "include", "pmt_ops.h")) as f:
+        text = re.sub(r"/\*.*?\*/", "", f.read(), flags=re.S)
+    return sorted(set(re.findall(r"\b(pmt_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_library_exports_every_declared_symbol(built):
+    lib = ctypes.CDLL(os.path.join(PKG, "libpmt_ops.so"))
+    names = declared_symbols()
+    assert len(names) >= 19
+    for n in names:
+        assert hasattr(lib, n), f"{n} declared in include/pmt_ops.h but not exported"
+    from pmt_learning_for_semantic_segmentation_and_disparity_b200 import _lib
+    assert sorted(_lib.EXPORTED_SYMBOLS) == names       # the ctypes table binds exactly the header
+    assert built.load_library().pmt_version() >= 100
+
+
+def test_argument_validation_without_gpu(built):
+    lib = built.load_library()
+    # null pointers / bad patch are rejected before anything touches a device
+    assert lib.pmt_corr1d_fwd_f32(None, None, None, 1, 1, 1, 4, 3, 1, None) != 0
+    assert b"null" in lib.pmt_last_error()
+    assert lib.pmt_softargmin_fwd_f32(None, None, None, 1, 4, 1, 4, None) != 0
+    assert lib.pmt_warp1d_bwd_f32(None, None, None, None, None, 1, 1, 1, 1, 0, None) != 0
+
+
+def test_shims_fail_loudly_on_cpu_tensors(built):
+    a = torch.zeros(1, 2, 3, 8)
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        built.SpatialCorrelationSampler(1, (1, 5), 1, 0, 1, 1)(a, a)
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        built.build_concat_volume(a, a, 3)
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        built.softargmin(a)
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        built.apply_disparity(a, torch.zeros(1, 1, 3, 8))
+    with pytest.raises(NotImplementedError):
+        built.SpatialCorrelationSampler(kernel_size=3, patch_size=1)(a, a)
+    assert built.apply_disparity(a, a, wrap_mode="other") is None   # reference returns None (torch_dsnet.py:21-22)
+
+
+def test_missing_library_is_an_error(built, monkeypatch):
+    from pmt_learning_for_semantic_segmentation_and_disparity_b200 import _lib
+    monkeypatch.setattr(_lib, "_lib", None)
+    monkeypatch.setattr(_lib, "LIB_PATH", os.path.join(PKG, "does_not_exist.so"))
+    with pytest.raises(RuntimeError, match="no CPU or PyTorch fallback"):
+        _lib.load()
+
+
+def test_compat_module_names(built):
+    built.install_reference_shims()
+    import spatial_correlation_sampler as scs
+    assert scs.SpatialCorrelationSampler is built.SpatialCorrelationSampler
+    s = scs.SpatialCorrelationSampler(kernel_size=1, patch_size=(1, 17), stride=1, padding=0, dilation_patch=1)
+    assert list(s.parameters()) == []
+    assert callable(scs.spatial_correlation_sample) and hasattr(scs, "SpatialCorrelationSamplerFunction")
+    del sys.modules["spatial_correlation_sampler"]
+
+
+def test_product_never_imports_oracle():
+    for dirpath, _, files in os.walk(PKG):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                with open(os.path.join(dirpath, f)) as fh:
+                    src = fh.read()
+                assert not re.search(r"^\s*(import|from)\s+oracle\b", src, flags=re.M), f
+                assert "libpmt_oracle" not in src, f
