@@ -8,7 +8,8 @@
 // G[w,w'] = sum_c L[c,w] R[c,w'] -- a GEMM with K=C whose operands are both "K-major rows", which is
 // exactly how NCHW rows sit in memory.  One CTA owns 64 output columns and all P shifts:
 //   * a producer warp streams 16-channel slabs of the L tile [16][64] and of the R band [16][BW]
-//     (BW = 56+8*NQ floats, = 256 for P=192) into a 3-stage shared-memory ring with TMA
+//     (BW = 56+8*NQ floats, = 256 for P=192; its first column is rounded down to a multiple of 4
+//     because TMA wants a 16-byte aligned inner start) into a 3-stage shared-memory ring with TMA
 //     (cp.async.bulk.tensor, 4-D map over (W,H,C,B)); TMA's zero OOB fill implements the sampler's
 //     "skip terms outside the image" (left/right halo, ragged last tile, C % 16) for free;
 //   * compute threads hold 8x8 register tiles of G: thread (s,q) owns rows w = 8s..8s+7 and the two
@@ -34,6 +35,8 @@ constexpr int kMaxThreads = 256;   // 7 compute warps (P<=193) + 1 producer warp
 
 struct FwdArgs {
   int C, H, W, P, rW;
+  int delta;      // band origin is rounded down to a multiple of 4 columns (TMA needs a 16-byte
+                  // aligned start in the innermost dimension): smem column j <-> w' = w0 - rW - delta + j
   int NQ;         // column-chunk pairs per strip
   int BW;         // R band width in floats (inner box dim of the R tensor map)
   int n_wtiles, n_cchunks;
@@ -84,7 +87,7 @@ corr1d_fwd_kernel(const __grid_constant__ CUtensorMap tmL, const __grid_constant
         float* Rs = Ls + kCK * kWT;
         mbar_arrive_expect_tx(&full[st], bytes);
         tma_load_4d(Ls, &tmL, w0, h, k * kCK, n, &full[st]);
-        tma_load_4d(Rs, &tmR, w0 - a.rW, h, k * kCK, n, &full[st]);
+        tma_load_4d(Rs, &tmR, w0 - a.rW - a.delta, h, k * kCK, n, &full[st]);
       }
     }
     return;
@@ -154,7 +157,7 @@ corr1d_fwd_kernel(const __grid_constant__ CUtensorMap tmL, const __grid_constant
       for (int i = 0; i < 8; ++i) {
 #pragma unroll
         for (int jj = 0; jj < 4; ++jj) {
-          const int p = 4 * u + jj - i;
+          const int p = 4 * u + jj - i - a.delta;
           if (p >= 0 && p < a.P) tile[p * kWT + ((8 * s + i + (p >> 2)) & (kWT - 1))] = acc[i][hf * 4 + jj];
         }
       }
@@ -177,7 +180,8 @@ corr1d_fwd_kernel(const __grid_constant__ CUtensorMap tmL, const __grid_constant
 
 bool corr1d_fwd_fast_ok(const void* in1, const void* in2, int W, int P, int dilp) {
   if (dilp != 1 || P < 1 || W % 4 != 0 || !aligned16(in1) || !aligned16(in2)) return false;
-  const int U = (P + 6) / 4 + 1, NQ = (U + 1) / 2;
+  const int rW = (P - 1) / 2, delta = ((-rW % 4) + 4) % 4;
+  const int U = (P + 6 + delta) / 4 + 1, NQ = (U + 1) / 2;
   return 8 * (kNS - 1) + 8 * NQ <= 256;  // TMA box limit
 }
 
@@ -185,7 +189,8 @@ int launch_corr1d_fwd_tiled(const float* in1, const float* in2, float* out, int 
                             int P, cudaStream_t st) {
   FwdArgs a;
   a.C = C, a.H = H, a.W = W, a.P = P, a.rW = (P - 1) / 2;
-  const int U = (P + 6) / 4 + 1;
+  a.delta = ((-a.rW % 4) + 4) % 4;
+  const int U = (P + 6 + a.delta) / 4 + 1;
   a.NQ = (U + 1) / 2;
   a.BW = 8 * (kNS - 1) + 8 * a.NQ;
   a.n_wtiles = ceil_div(W, kWT);
