@@ -54,6 +54,12 @@ int pmt_corr1d_fwd_f32(const float* in1, const float* in2, float* out, int B, in
                        int P, int dilp, void* stream);
 int pmt_corr1d_bwd_f32(const float* in1, const float* in2, const float* gout, float* gin1,
                        float* gin2, int B, int C, int H, int W, int P, int dilp, void* stream);
+/* Tensor-core forward of the 1 x P correlation (tcgen05.mma kind::tf32, accumulator in TMEM).
+ *   passes = 1: plain TF32 inputs (reduced-precision variant, ~1e-3 relative);
+ *   passes = 3: 3xTF32 split (hi*hi + hi*lo + lo*hi), fp32-class accuracy (<= 1e-5 relative).
+ * Returns PMT_ERR_UNSUPPORTED when the shape/alignment does not fit (no fallback inside). */
+int pmt_corr1d_fwd_tc_f32(const float* in1, const float* in2, float* out, int B, int C, int H, int W,
+                          int P, int dilp, int passes, void* stream);
 int pmt_corr_fwd_f32(const float* in1, const float* in2, float* out, int B, int C, int H, int W,
                      int patchH, int patchW, int dilpH, int dilpW, void* stream);
 int pmt_corr_bwd_f32(const float* in1, const float* in2, const float* gout, float* gin1,

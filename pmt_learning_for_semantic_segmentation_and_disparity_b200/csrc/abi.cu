@@ -18,6 +18,8 @@ int launch_corr1d_fwd_tiled(const float*, const float*, float*, int, int, int, i
 bool corr1d_bwd_fast_ok(const void*, const void*, const void*, int C, int W, int P, int dilp);
 int launch_corr1d_bwd_tiled(const float*, const float*, const float*, float*, float*, int, int, int,
                             int, int, cudaStream_t);
+bool corr1d_fwd_tc_ok(const void*, const void*, const void*, int C, int H, int W, int P, int dilp, int passes);
+int launch_corr1d_fwd_tc(const float*, const float*, float*, int, int, int, int, int, int, cudaStream_t);
 int launch_concat_fwd(const float*, const float*, float*, int, int, int, int, int, int, cudaStream_t);
 int launch_concat_bwd(const float*, float*, float*, int, int, int, int, int, int, cudaStream_t);
 int launch_softargmin_fwd(const float*, float*, float*, int, int, int, int, cudaStream_t);
@@ -70,8 +72,16 @@ static EncodeTiledFn encode_tiled_fn() {
   return fn;
 }
 
+int make_tmap_nchw_ex(CUtensorMap* map, const float* base, int B, int C, int H, int W, int box_w, int box_c,
+                      int swizzle128);
+
 int make_tmap_nchw(CUtensorMap* map, const float* base, int B, int C, int H, int W, int box_w,
                    int box_c) {
+  return make_tmap_nchw_ex(map, base, B, C, H, W, box_w, box_c, 0);
+}
+
+int make_tmap_nchw_ex(CUtensorMap* map, const float* base, int B, int C, int H, int W, int box_w, int box_c,
+                      int swizzle128) {
   EncodeTiledFn enc = encode_tiled_fn();
   if (enc == nullptr) {
     set_error("cuTensorMapEncodeTiled not available from the driver");
@@ -82,7 +92,9 @@ int make_tmap_nchw(CUtensorMap* map, const float* base, int B, int C, int H, int
   const cuuint32_t box[4] = {(cuuint32_t)box_w, 1u, (cuuint32_t)box_c, 1u};
   const cuuint32_t estr[4] = {1u, 1u, 1u, 1u};
   const CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(base), dims, strides,
-                         box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                         box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                         swizzle128 == 2 ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B
+                         : swizzle128 == 1 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE,
                          CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     set_error("cuTensorMapEncodeTiled failed (CUresult %d) for dims (%d,%d,%d,%d) box (%d,1,%d,1)", (int)r,
@@ -166,6 +178,18 @@ int pmt_corr1d_fwd_f32(const float* in1, const float* in2, float* out, int B, in
   if (C > 0 && corr1d_fwd_fast_ok(in1, in2, W, P, dilp))
     return launch_corr1d_fwd_tiled(in1, in2, out, B, C, H, W, P, st);
   return launch_corr_generic_fwd(in1, in2, out, B, C, H, W, 1, P, 1, dilp, st);
+}
+
+int pmt_corr1d_fwd_tc_f32(const float* in1, const float* in2, float* out, int B, int C, int H, int W, int P,
+                          int dilp, int passes, void* stream) {
+  if (int e = check_corr_args(in1, in2, out, B, C, H, W, 1, P, 1, dilp)) return e;
+  PMT_CHECK_ARG(passes == 1 || passes == 3, "corr1d tc: passes must be 1 (tf32) or 3 (3xtf32)");
+  if ((int64_t)B * H * W == 0) return PMT_OK;
+  if (!corr1d_fwd_tc_ok(in1, in2, out, C, H, W, P, dilp, passes)) {
+    set_error("corr1d tc: shape/alignment not supported by the tensor-core path (W%%4, 16-byte pointers, P<=193, dilp=1)");
+    return PMT_ERR_UNSUPPORTED;
+  }
+  return launch_corr1d_fwd_tc(in1, in2, out, B, C, H, W, P, passes, static_cast<cudaStream_t>(stream));
 }
 
 int pmt_corr1d_bwd_f32(const float* in1, const float* in2, const float* gout, float* gin1, float* gin2,

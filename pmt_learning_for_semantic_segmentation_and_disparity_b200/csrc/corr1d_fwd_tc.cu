@@ -1,0 +1,293 @@
+// corr1d_fwd_tc.cu -- tensor-core (tcgen05 + TMEM) forward of the 1 x P horizontal correlation.
+//
+// Per image row the op is the band of the Gram matrix G[w,w'] = sum_c L[c,w] R[c,w'].  NCHW rows are
+// "MN-major" operands (w contiguous, channel = K strided), which tcgen05.mma kind::tf32 reads straight
+// from shared memory, so fp32 features go TMA -> SWIZZLE_128B smem -> tensor core with no cast pass:
+//   * CTA tile = 128 output columns x the whole band (N = 32*NB columns, 320 for P=192); accumulator
+//     D[128 lanes][N cols] fp32 lives in TMEM;
+//   * warp 0 streams 16-channel slabs (boxes of 32 columns x 16 channels, 2 KB, 128-byte swizzle) of
+//     the L tile and the R band through a ring with TMA; warp 1 issues tcgen05.mma (M=128, N<=256,
+//     K=8 per instruction) and commits to mbarriers; 4 epilogue warps read TMEM with tcgen05.ld, un-skew
+//     D[w][j] -> out[p = j - w - delta][w] into a dense [P][128] staging tile (bank-conflict free: the
+//     row stride is 128 words) and ONE TMA store writes the whole tile;
+//   * kPasses = 1: plain TF32 (10-bit mantissa inputs, fp32 accumulate) -- the reduced-precision variant;
+//     kPasses = 3: "3xTF32": 4 transform warps split every staged value into hi = tf32(x), lo = x - hi
+//     (exact in fp32) and the MMA warp accumulates hi*hi + hi*lo + lo*hi, recovering fp32-class
+//     accuracy (error ~2^-22 per product) at 3x the tensor work, still far below the FP32-pipe time.
+#include <stdlib.h>
+
+#include "tc_common.cuh"
+
+namespace pmt {
+namespace {
+
+constexpr int kTM = 128;              // output columns per CTA (= UMMA M = TMEM lanes)
+constexpr int kCK = 16;               // channels per ring stage (2 k-steps of 8)
+constexpr int kBoxBytes = kCK * 128;  // one 32-column x 16-channel box
+constexpr int kLBlocks = kTM / 32;    // 4 boxes for the L tile
+constexpr int kMaxNB = 10;            // band boxes (P <= 193)
+
+struct TcFwdArgs {
+  int C, H, W, P, rW, delta;
+  int NB;                // band boxes of 32 columns
+  int N1, N2;            // MMA N of the two band halves (N2 may be 0)
+  int tmem_cols;         // power of two >= 32*NB
+  int n_wtiles, n_cchunks;
+  int stages;
+  int stage_bytes;       // (4+NB)*kBoxBytes * (hi+lo ? 2 : 1)
+  int lo_off;            // byte offset of the lo copy inside a stage
+  int tile_off;          // byte offset of the [P][128] staging tile
+  int bar_off;           // byte offset of the barriers
+  int debug;             // PMT_TC_DEBUG: 1 = constant tile, 2 = tcgen05.st pattern instead of MMA result
+};
+
+// MN-major tf32 operand: 32 columns x 4 channel rows per swizzle atom (Swizzle<2,5,2>, 128-byte rows),
+// column blocks kBoxBytes apart (LBO), 4-row k-groups 512 bytes apart (SBO).
+__device__ __forceinline__ uint64_t mn_desc(uint32_t saddr, uint32_t lbo, uint32_t) {
+  return tc::smem_desc(saddr, lbo, 512, 1);
+}
+
+template <int kPasses>
+__global__ void __launch_bounds__(kPasses == 3 ? 320 : 192, 1)
+corr1d_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmL, const __grid_constant__ CUtensorMap tmR,
+                     const __grid_constant__ CUtensorMap tmO, const TcFwdArgs a) {
+  extern __shared__ __align__(1024) unsigned char smem[];
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + a.bar_off);
+  uint64_t* empty = full + 8;
+  uint64_t* xf_done = empty + 8;
+  uint64_t* tmem_full = xf_done + 8;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + 1);
+
+  const int tid = threadIdx.x, wid = tid >> 5, lane = tid & 31;
+  int bid = blockIdx.x;
+  const int wt = bid % a.n_wtiles;
+  bid /= a.n_wtiles;
+  const int h = bid % a.H;
+  const int n = bid / a.H;
+  const int w0 = wt * kTM;
+  const int nboxes = kLBlocks + a.NB;
+
+  if (tid == 0) {
+    for (int s = 0; s < a.stages; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], 1);
+      mbar_init(&xf_done[s], 4);
+    }
+    mbar_init(tmem_full, 1);
+    fence_mbar_init();
+  }
+  if (wid == 1) {
+    tc::tmem_alloc(tmem_slot, (uint32_t)a.tmem_cols);
+    tc::tmem_relinquish();
+  }
+  tc::fence_before_sync();
+  __syncthreads();
+  tc::fence_after_sync();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (wid == 0) {
+    // ===== TMA producer =====
+    if (lane == 0) {
+      tma_prefetch_desc(&tmL);
+      tma_prefetch_desc(&tmR);
+    }
+    const uint32_t bytes = (uint32_t)nboxes * kBoxBytes;
+    for (int k = 0; k < a.n_cchunks; ++k) {
+      const int st = k % a.stages;
+      const uint32_t ph = (uint32_t)(k / a.stages) & 1u;
+      mbar_wait(&empty[st], ph ^ 1u);
+      unsigned char* sbase = smem + (size_t)st * a.stage_bytes;
+      if (lane == 0) mbar_arrive_expect_tx(&full[st], bytes);
+      __syncwarp();
+      if (lane < nboxes) {
+        if (lane < kLBlocks)
+          tma_load_4d(sbase + lane * kBoxBytes, &tmL, w0 + 32 * lane, h, k * kCK, n, &full[st]);
+        else
+          tma_load_4d(sbase + lane * kBoxBytes, &tmR, w0 - a.rW - a.delta + 32 * (lane - kLBlocks), h, k * kCK, n,
+                      &full[st]);
+      }
+    }
+  } else if (wid == 1) {
+    // ===== MMA issuer (one elected lane) =====
+    if (lane == 0) {
+      const uint32_t idesc1 = tc::make_idesc(2, 1, 1, kTM, a.N1);
+      const uint32_t idesc2 = tc::make_idesc(2, 1, 1, kTM, a.N2 > 0 ? a.N2 : 16);
+      const int nb1 = a.N1 / 32;
+      for (int k = 0; k < a.n_cchunks; ++k) {
+        const int st = k % a.stages;
+        const uint32_t ph = (uint32_t)(k / a.stages) & 1u;
+        mbar_wait(kPasses == 3 ? &xf_done[st] : &full[st], ph);
+        tc::fence_after_sync();
+        const uint32_t sbase = smem_u32(smem + (size_t)st * a.stage_bytes);
+#pragma unroll
+        for (int kk = 0; kk < kCK / 8; ++kk) {
+          const uint32_t acc = (k > 0 || kk > 0) ? 1u : 0u;
+          const uint32_t a_hi = sbase + kk * 1024;
+          const uint32_t b1_hi = sbase + kLBlocks * kBoxBytes + kk * 1024;
+          const uint32_t b2_hi = b1_hi + nb1 * kBoxBytes;
+          const uint64_t dA = mn_desc(a_hi, kBoxBytes, 1024);
+          const uint64_t dB1 = mn_desc(b1_hi, kBoxBytes, 1024);
+          const uint64_t dB2 = mn_desc(b2_hi, kBoxBytes, 1024);
+          if (kPasses == 3) {
+            const uint64_t dAl = mn_desc(a_hi + a.lo_off, kBoxBytes, 1024);
+            const uint64_t dB1l = mn_desc(b1_hi + a.lo_off, kBoxBytes, 1024);
+            const uint64_t dB2l = mn_desc(b2_hi + a.lo_off, kBoxBytes, 1024);
+            // small cross terms first, then the dominant hi*hi term
+            tc::mma_tf32(tmem_base, dAl, dB1, idesc1, acc);
+            tc::mma_tf32(tmem_base, dA, dB1l, idesc1, 1u);
+            tc::mma_tf32(tmem_base, dA, dB1, idesc1, 1u);
+            if (a.N2 > 0) {
+              tc::mma_tf32(tmem_base + a.N1, dAl, dB2, idesc2, acc);
+              tc::mma_tf32(tmem_base + a.N1, dA, dB2l, idesc2, 1u);
+              tc::mma_tf32(tmem_base + a.N1, dA, dB2, idesc2, 1u);
+            }
+          } else {
+            tc::mma_tf32(tmem_base, dA, dB1, idesc1, acc);
+            if (a.N2 > 0) tc::mma_tf32(tmem_base + a.N1, dA, dB2, idesc2, acc);
+          }
+        }
+        tc::mma_commit(&empty[st]);  // ring slot reusable once these MMAs have read it
+      }
+      tc::mma_commit(tmem_full);     // accumulator complete
+    }
+  } else if (wid < 6) {
+    // ===== epilogue warps: TMEM -> registers -> un-skewed staging tile -> TMA store =====
+    const int q = wid & 3;               // TMEM lane quarter this warp may access
+    const int wl = 32 * q + lane;        // output column within the tile (= TMEM lane)
+    float* tile = reinterpret_cast<float*>(smem + a.tile_off);
+    mbar_wait(tmem_full, 0);
+    tc::fence_after_sync();
+    const int c_lo = (32 * q + a.delta) / 32;
+    int c_hi = (32 * q + 31 + a.delta + a.P - 1) / 32;
+    if (c_hi > a.NB - 1) c_hi = a.NB - 1;
+    for (int cb = c_lo; cb <= c_hi; ++cb) {
+      float v[32];
+      if (a.debug == 2) {
+        // write a lane/column pattern with tcgen05.st, then read it back
+        for (int jj = 0; jj < 32; ++jj) {
+          const uint32_t val = __float_as_uint((float)(wl * 1000 + 32 * cb + jj));
+          asm volatile("tcgen05.st.sync.aligned.32x32b.x1.b32 [%0], {%1};" ::"r"(tmem_base + ((uint32_t)(32 * q) << 16) + (uint32_t)(32 * cb + jj)), "r"(val) : "memory");
+        }
+        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+      }
+      tc::tmem_ld32(tmem_base + ((uint32_t)(32 * q) << 16) + (uint32_t)(32 * cb), v);
+      if (a.debug == 1) {
+        for (int jj = 0; jj < 32; ++jj) v[jj] = (float)(wl * 1000 + 32 * cb + jj);
+      }
+      const int pbase = 32 * cb - a.delta - wl;  // p of column jj is pbase + jj
+#pragma unroll
+      for (int jj = 0; jj < 32; ++jj) {
+        const int p = pbase + jj;
+        if (p >= 0 && p < a.P) tile[p * kTM + wl] = v[jj];
+      }
+    }
+    fence_proxy_async();           // generic-proxy writes -> visible to the TMA store
+    named_bar_sync(1, 128);
+    if (wid == 2 && lane == 0) {
+      tc::tma_store_4d(&tmO, tile, w0, h, 0, n);
+      tc::tma_store_commit();
+      tc::tma_store_wait_read<0>();
+    }
+  } else {
+    // ===== transform warps (kPasses == 3): split staged fp32 into tf32 hi + lo =====
+    const int t = tid - 6 * 32;  // 0..127
+    const int nchunks = nboxes * (kBoxBytes / 16);
+    for (int k = 0; k < a.n_cchunks; ++k) {
+      const int st = k % a.stages;
+      const uint32_t ph = (uint32_t)(k / a.stages) & 1u;
+      mbar_wait(&full[st], ph);
+      unsigned char* sbase = smem + (size_t)st * a.stage_bytes;
+      for (int c = t; c < nchunks; c += 128) {
+        float4* p = reinterpret_cast<float4*>(sbase + 16 * c);
+        const float4 x = *p;
+        float4 hi, lo;
+        uint32_t u;
+        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x.x)); hi.x = __uint_as_float(u); lo.x = x.x - hi.x;
+        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x.y)); hi.y = __uint_as_float(u); lo.y = x.y - hi.y;
+        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x.z)); hi.z = __uint_as_float(u); lo.z = x.z - hi.z;
+        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x.w)); hi.w = __uint_as_float(u); lo.w = x.w - hi.w;
+        *p = hi;
+        *reinterpret_cast<float4*>(sbase + a.lo_off + 16 * c) = lo;
+      }
+      fence_proxy_async();  // make the rewritten stage visible to the tensor core's async-proxy reads
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&xf_done[st]);
+    }
+  }
+
+  tc::fence_before_sync();
+  __syncthreads();
+  if (wid == 1) {
+    tc::fence_after_sync();
+    tc::tmem_dealloc(tmem_base, (uint32_t)a.tmem_cols);
+  }
+}
+
+int fill_args(TcFwdArgs* a, int C, int H, int W, int P, int passes) {
+  a->C = C, a->H = H, a->W = W, a->P = P, a->rW = (P - 1) / 2;
+  a->delta = ((-a->rW % 4) + 4) % 4;
+  a->NB = ceil_div(kTM + P - 1 + a->delta, 32);
+  if (a->NB > kMaxNB) return 1;
+  const int nb1 = (a->NB + 1) / 2;
+  a->N1 = 32 * nb1;
+  a->N2 = 32 * (a->NB - nb1);
+  int cols = 32;
+  while (cols < 32 * a->NB) cols *= 2;
+  a->tmem_cols = cols;
+  a->n_wtiles = ceil_div(W, kTM);
+  a->n_cchunks = ceil_div(C, kCK);
+  const int hi_bytes = (kLBlocks + a->NB) * kBoxBytes;
+  a->lo_off = hi_bytes;
+  a->stage_bytes = hi_bytes * (passes == 3 ? 2 : 1);
+  const int tile_bytes = round_up(P * kTM * 4, 1024);
+  const int budget = 227 * 1024 - 512 - tile_bytes;
+  int stages = budget / a->stage_bytes;
+  if (stages > 8) stages = 8;
+  if (stages > a->n_cchunks) stages = a->n_cchunks;
+  if (stages < 1) return 1;
+  a->stages = stages;
+  a->tile_off = stages * a->stage_bytes;
+  a->bar_off = a->tile_off + tile_bytes;
+  const char* dbg = getenv("PMT_TC_DEBUG");
+  a->debug = dbg ? atoi(dbg) : 0;
+  return 0;
+}
+
+}  // namespace
+
+int make_tmap_nchw_ex(CUtensorMap* map, const float* base, int B, int C, int H, int W, int box_w, int box_c,
+                      int swizzle128);
+
+bool corr1d_fwd_tc_ok(const void* in1, const void* in2, const void* out, int C, int H, int W, int P, int dilp,
+                      int passes) {
+  if (dilp != 1 || P < 1 || C < 1 || W % 4 != 0 || !aligned16(in1) || !aligned16(in2) || !aligned16(out)) return false;
+  if (P > 256) return false;  // TMA store box limit
+  TcFwdArgs a;
+  (void)H;
+  return fill_args(&a, C, H, W, P, passes) == 0;
+}
+
+int launch_corr1d_fwd_tc(const float* in1, const float* in2, float* out, int B, int C, int H, int W, int P,
+                         int passes, cudaStream_t st) {
+  TcFwdArgs a;
+  PMT_CHECK_ARG(passes == 1 || passes == 3, "corr1d tc: passes must be 1 (tf32) or 3 (3xtf32)");
+  PMT_CHECK_ARG(fill_args(&a, C, H, W, P, passes) == 0, "corr1d tc: unsupported shape P=%d", P);
+  CUtensorMap tmL, tmR, tmO;
+  if (int e = make_tmap_nchw_ex(&tmL, in1, B, C, H, W, 32, kCK, 2)) return e;
+  if (int e = make_tmap_nchw_ex(&tmR, in2, B, C, H, W, 32, kCK, 2)) return e;
+  if (int e = make_tmap_nchw_ex(&tmO, out, B, P, H, W, kTM, P, 0)) return e;
+  const int smem_bytes = a.bar_off + 512;
+  const int64_t grid = (int64_t)B * H * a.n_wtiles;
+  PMT_CHECK_ARG(grid < (1ll << 31), "corr1d tc: grid too large");
+  if (passes == 3) {
+    PMT_CUDA_OK(cudaFuncSetAttribute(corr1d_fwd_tc_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
+    corr1d_fwd_tc_kernel<3><<<(unsigned)grid, 320, smem_bytes, st>>>(tmL, tmR, tmO, a);
+  } else {
+    PMT_CUDA_OK(cudaFuncSetAttribute(corr1d_fwd_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
+    corr1d_fwd_tc_kernel<1><<<(unsigned)grid, 192, smem_bytes, st>>>(tmL, tmR, tmO, a);
+  }
+  PMT_LAUNCH_OK("corr1d_fwd_tc_kernel");
+  return PMT_OK;
+}
+
+}  // namespace pmt
