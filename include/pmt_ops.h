@@ -60,6 +60,9 @@ int pmt_corr1d_bwd_f32(const float* in1, const float* in2, const float* gout, fl
  * Returns PMT_ERR_UNSUPPORTED when the shape/alignment does not fit (no fallback inside). */
 int pmt_corr1d_fwd_tc_f32(const float* in1, const float* in2, float* out, int B, int C, int H, int W,
                           int P, int dilp, int passes, void* stream);
+int pmt_corr1d_bwd_tc_f32(const float* in1, const float* in2, const float* gout, float* gin1,
+                          float* gin2, int B, int C, int H, int W, int P, int dilp, int passes,
+                          void* stream);
 int pmt_corr_fwd_f32(const float* in1, const float* in2, float* out, int B, int C, int H, int W,
                      int patchH, int patchW, int dilpH, int dilpW, void* stream);
 int pmt_corr_bwd_f32(const float* in1, const float* in2, const float* gout, float* gin1,

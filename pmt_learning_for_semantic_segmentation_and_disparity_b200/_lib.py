@@ -22,6 +22,7 @@ _SIGNATURES = {
     "pmt_corr1d_fwd_f32": [_P, _P, _P, _I, _I, _I, _I, _I, _I, _P],
     "pmt_corr1d_bwd_f32": [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P],
     "pmt_corr1d_fwd_tc_f32": [_P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P],
+    "pmt_corr1d_bwd_tc_f32": [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P],
     "pmt_corr_fwd_f32": [_P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _P],
     "pmt_corr_bwd_f32": [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _P],
     "pmt_corr1d_uses_fast_path": [_P, _P, _P, _I, _I, _I, _I, _I],

@@ -20,6 +20,9 @@ int launch_corr1d_bwd_tiled(const float*, const float*, const float*, float*, fl
                             int, int, cudaStream_t);
 bool corr1d_fwd_tc_ok(const void*, const void*, const void*, int C, int H, int W, int P, int dilp, int passes);
 int launch_corr1d_fwd_tc(const float*, const float*, float*, int, int, int, int, int, int, cudaStream_t);
+bool corr1d_bwd_tc_ok(const void*, const void*, int C, int H, int W, int P, int dilp, int passes);
+int launch_corr1d_bwd_tc(const float*, const float*, const float*, float*, float*, int, int, int, int, int, int,
+                         cudaStream_t);
 int launch_concat_fwd(const float*, const float*, float*, int, int, int, int, int, int, cudaStream_t);
 int launch_concat_bwd(const float*, float*, float*, int, int, int, int, int, int, cudaStream_t);
 int launch_softargmin_fwd(const float*, float*, float*, int, int, int, int, cudaStream_t);
@@ -190,6 +193,19 @@ int pmt_corr1d_fwd_tc_f32(const float* in1, const float* in2, float* out, int B,
     return PMT_ERR_UNSUPPORTED;
   }
   return launch_corr1d_fwd_tc(in1, in2, out, B, C, H, W, P, passes, static_cast<cudaStream_t>(stream));
+}
+
+int pmt_corr1d_bwd_tc_f32(const float* in1, const float* in2, const float* gout, float* gin1, float* gin2, int B,
+                          int C, int H, int W, int P, int dilp, int passes, void* stream) {
+  if (int e = check_corr_args(in1, in2, gout, B, C, H, W, 1, P, 1, dilp)) return e;
+  PMT_CHECK_ARG(gin1 && gin2, "correlation backward: null gradient pointer");
+  PMT_CHECK_ARG(passes == 1 || passes == 3, "corr1d tc: passes must be 1 (tf32) or 3 (3xtf32)");
+  if ((int64_t)B * C * H * W == 0) return PMT_OK;
+  if (!corr1d_bwd_tc_ok(in1, in2, C, H, W, P, dilp, passes)) {
+    set_error("corr1d tc bwd: shape/alignment not supported by the tensor-core path (W%%4, 16-byte pointers, C<=128, dilp=1)");
+    return PMT_ERR_UNSUPPORTED;
+  }
+  return launch_corr1d_bwd_tc(in1, in2, gout, gin1, gin2, B, C, H, W, P, passes, static_cast<cudaStream_t>(stream));
 }
 
 int pmt_corr1d_bwd_f32(const float* in1, const float* in2, const float* gout, float* gin1, float* gin2,
