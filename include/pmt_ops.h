@@ -44,9 +44,12 @@ int pmt_device_supported(int dev);
  *   out[n,ph,pw,h,w] = sum_c in1[n,c,h,w] * in2[n,c,h+sh,w+sw]   (terms outside the image skipped)
  *   sh = (ph-(patchH-1)/2)*dilpH, sw = (pw-(patchW-1)/2)*dilpW;  out is (B,patchH,patchW,H,W).
  *
- * pmt_corr1d_*: the 1 x P horizontal patch (the hot path; `-corrType 1dcorr`).  Dispatches to the
- *   TMA-tiled register-blocked kernels when W%4==0, pointers are 16-byte aligned, dilp==1 and
- *   P<=193; otherwise to the generic CUDA kernels below.  Backward is a deterministic gather.
+ * pmt_corr1d_{fwd,bwd}_f32: the 1 x P horizontal patch (the hot path; `-corrType 1dcorr`), fp32-accurate
+ *   results from the fastest engine that fits: tensor cores with the 3xTF32 split (W%4==0, 16-byte
+ *   pointers, dilp==1, P<=193, C<=128 for the backward) -> CUDA-core TMA-tiled kernels -> generic
+ *   kernels.  Backward is a deterministic gather on every engine (bit-reproducible run to run).
+ * pmt_corr1d_{fwd,bwd}_simt_f32: force the CUDA-core engines (fp32 FFMA).
+ * pmt_corr1d_{fwd,bwd}_tc_f32: force the tensor-core engine (see below).
  * pmt_corr_*: any (patchH, patchW, dilation_patch) -- generic CUDA kernels (2-D 17x17 patches of
  *   `-corrType 2dcorr`, the (1,21) dilation_patch=4 sampler of torch_dsnet.py:133-138).
  * ------------------------------------------------------------------------------------------- */
@@ -54,7 +57,11 @@ int pmt_corr1d_fwd_f32(const float* in1, const float* in2, float* out, int B, in
                        int P, int dilp, void* stream);
 int pmt_corr1d_bwd_f32(const float* in1, const float* in2, const float* gout, float* gin1,
                        float* gin2, int B, int C, int H, int W, int P, int dilp, void* stream);
-/* Tensor-core forward of the 1 x P correlation (tcgen05.mma kind::tf32, accumulator in TMEM).
+int pmt_corr1d_fwd_simt_f32(const float* in1, const float* in2, float* out, int B, int C, int H, int W,
+                            int P, int dilp, void* stream);
+int pmt_corr1d_bwd_simt_f32(const float* in1, const float* in2, const float* gout, float* gin1,
+                            float* gin2, int B, int C, int H, int W, int P, int dilp, void* stream);
+/* Tensor-core forward/backward of the 1 x P correlation (tcgen05.mma kind::tf32, accumulator in TMEM).
  *   passes = 1: plain TF32 inputs (reduced-precision variant, ~1e-3 relative);
  *   passes = 3: 3xTF32 split (hi*hi + hi*lo + lo*hi), fp32-class accuracy (<= 1e-5 relative).
  * Returns PMT_ERR_UNSUPPORTED when the shape/alignment does not fit (no fallback inside). */
@@ -68,7 +75,7 @@ int pmt_corr_fwd_f32(const float* in1, const float* in2, float* out, int B, int 
 int pmt_corr_bwd_f32(const float* in1, const float* in2, const float* gout, float* gin1,
                      float* gin2, int B, int C, int H, int W, int patchH, int patchW, int dilpH,
                      int dilpW, void* stream);
-/* which kernel family pmt_corr1d_* would use for this problem: 1 = tiled fast path, 0 = generic */
+/* which engine pmt_corr1d_{fwd,bwd}_f32 would use: 2 = tensor core (3xTF32), 1 = CUDA-core tiled, 0 = generic */
 int pmt_corr1d_uses_fast_path(const void* in1, const void* in2, const void* out_or_gout, int C,
                               int H, int W, int P, int dilp);
 

@@ -6,7 +6,7 @@ include/pmt_ops.h.  There is no CPU, PyTorch-eager or Triton fallback: if the li
 """
 from ._lib import PmtOpsError, load as load_library  # noqa: F401
 from .correlation import (SpatialCorrelationSampler, SpatialCorrelationSamplerFunction,  # noqa: F401
-                          spatial_correlation_sample)
+                          get_correlation_engine, set_correlation_engine, spatial_correlation_sample)
 from .psmnet import build_concat_volume, disparityregression, matchshifted, softargmin  # noqa: F401
 from .warp import apply_disparity  # noqa: F401
 from .compat import install_reference_shims  # noqa: F401

@@ -21,6 +21,8 @@ _P = ctypes.c_void_p
 _SIGNATURES = {
     "pmt_corr1d_fwd_f32": [_P, _P, _P, _I, _I, _I, _I, _I, _I, _P],
     "pmt_corr1d_bwd_f32": [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P],
+    "pmt_corr1d_fwd_simt_f32": [_P, _P, _P, _I, _I, _I, _I, _I, _I, _P],
+    "pmt_corr1d_bwd_simt_f32": [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P],
     "pmt_corr1d_fwd_tc_f32": [_P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P],
     "pmt_corr1d_bwd_tc_f32": [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P],
     "pmt_corr_fwd_f32": [_P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _P],

@@ -20,6 +20,28 @@ from torch.autograd.function import once_differentiable
 
 from . import _util as U
 
+# Engine used for the 1 x P horizontal patch (the hot path):
+#   "auto" : fp32-accurate, fastest engine that fits (tensor cores with the 3xTF32 split -> CUDA-core
+#            tiled -> generic); this is the drop-in default.
+#   "simt" : force the CUDA-core (fp32 FFMA) kernels.
+#   "tf32" : plain-TF32 tensor-core variant (~1e-3 relative, the reduced-precision option that plays the
+#            role of north_star's bf16 variant); raises if the shape does not fit -- never a silent fallback.
+_ENGINES = ("auto", "simt", "tf32")
+_engine = "auto"
+
+
+def set_correlation_engine(name: str) -> str:
+    """Select the engine for 1 x P correlations; returns the previous setting."""
+    global _engine
+    if name not in _ENGINES:
+        raise ValueError(f"engine must be one of {_ENGINES}, got {name!r}")
+    prev, _engine = _engine, name
+    return prev
+
+
+def get_correlation_engine() -> str:
+    return _engine
+
 
 def _check_supported(kernel_size, stride, padding, dilation):
     kH, kW = U.pair(kernel_size, "kernel_size")
@@ -51,8 +73,15 @@ class SpatialCorrelationSamplerFunction(Function):
         B, C, H, W = in1.shape
         ctx.save_for_backward(in1, in2)
         ctx.patch = (pH, pW, dpH, dpW)
+        engine = _engine if pH == 1 else "auto"
+        ctx.engine = engine
         out = torch.empty((B, pH, pW, H, W), device=dev, dtype=torch.float32)
-        U.call("pmt_corr_fwd_f32", dev, U.ptr(in1), U.ptr(in2), U.ptr(out), B, C, H, W, pH, pW, dpH, dpW)
+        if engine == "simt":
+            U.call("pmt_corr1d_fwd_simt_f32", dev, U.ptr(in1), U.ptr(in2), U.ptr(out), B, C, H, W, pW, dpW)
+        elif engine == "tf32":
+            U.call("pmt_corr1d_fwd_tc_f32", dev, U.ptr(in1), U.ptr(in2), U.ptr(out), B, C, H, W, pW, dpW, 1)
+        else:
+            U.call("pmt_corr_fwd_f32", dev, U.ptr(in1), U.ptr(in2), U.ptr(out), B, C, H, W, pH, pW, dpH, dpW)
         return out
 
     @staticmethod
@@ -64,8 +93,13 @@ class SpatialCorrelationSamplerFunction(Function):
         g = U.require_cuda_f32(grad_output, "grad_output")
         g1 = torch.empty_like(in1)
         g2 = torch.empty_like(in2)
-        U.call("pmt_corr_bwd_f32", in1.device, U.ptr(in1), U.ptr(in2), U.ptr(g), U.ptr(g1), U.ptr(g2), B, C, H, W,
-               pH, pW, dpH, dpW)
+        args = (U.ptr(in1), U.ptr(in2), U.ptr(g), U.ptr(g1), U.ptr(g2), B, C, H, W)
+        if ctx.engine == "simt":
+            U.call("pmt_corr1d_bwd_simt_f32", in1.device, *args, pW, dpW)
+        elif ctx.engine == "tf32":
+            U.call("pmt_corr1d_bwd_tc_f32", in1.device, *args, pW, dpW, 1)
+        else:
+            U.call("pmt_corr_bwd_f32", in1.device, *args, pH, pW, dpH, dpW)
         return g1, g2, None, None, None, None, None, None
 
 

@@ -169,18 +169,51 @@ static int check_corr_args(const void* a, const void* b, const void* c, int B, i
 
 int pmt_corr1d_uses_fast_path(const void* in1, const void* in2, const void* third, int C, int H, int W,
                               int P, int dilp) {
-  (void)H;
+  if (corr1d_fwd_tc_ok(in1, in2, third, C, H, W, P, dilp, 3) && corr1d_bwd_tc_ok(in1, in2, C, H, W, P, dilp, 3)) return 2;
   return (corr1d_fwd_fast_ok(in1, in2, W, P, dilp) && corr1d_bwd_fast_ok(in1, in2, third, C, W, P, dilp)) ? 1 : 0;
 }
 
-int pmt_corr1d_fwd_f32(const float* in1, const float* in2, float* out, int B, int C, int H, int W, int P,
-                       int dilp, void* stream) {
+// CUDA-core (fp32 FFMA) engines: TMA-tiled register-blocked kernels, generic kernels otherwise.
+int pmt_corr1d_fwd_simt_f32(const float* in1, const float* in2, float* out, int B, int C, int H, int W, int P,
+                            int dilp, void* stream) {
   if (int e = check_corr_args(in1, in2, out, B, C, H, W, 1, P, 1, dilp)) return e;
   if ((int64_t)B * H * W == 0) return PMT_OK;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (C > 0 && corr1d_fwd_fast_ok(in1, in2, W, P, dilp))
     return launch_corr1d_fwd_tiled(in1, in2, out, B, C, H, W, P, st);
   return launch_corr_generic_fwd(in1, in2, out, B, C, H, W, 1, P, 1, dilp, st);
+}
+
+int pmt_corr1d_bwd_simt_f32(const float* in1, const float* in2, const float* gout, float* gin1, float* gin2,
+                            int B, int C, int H, int W, int P, int dilp, void* stream) {
+  if (int e = check_corr_args(in1, in2, gout, B, C, H, W, 1, P, 1, dilp)) return e;
+  PMT_CHECK_ARG(gin1 && gin2, "correlation backward: null gradient pointer");
+  if ((int64_t)B * C * H * W == 0) return PMT_OK;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (corr1d_bwd_fast_ok(in1, in2, gout, C, W, P, dilp) && aligned16(gin1) && aligned16(gin2))
+    return launch_corr1d_bwd_tiled(in1, in2, gout, gin1, gin2, B, C, H, W, P, st);
+  return launch_corr_generic_bwd(in1, in2, gout, gin1, gin2, B, C, H, W, 1, P, 1, dilp, st);
+}
+
+// Default entry points: fp32-accurate results from the fastest engine that fits
+// (tensor cores with the 3xTF32 split -> CUDA-core tiled -> generic).
+int pmt_corr1d_fwd_f32(const float* in1, const float* in2, float* out, int B, int C, int H, int W, int P,
+                       int dilp, void* stream) {
+  if (int e = check_corr_args(in1, in2, out, B, C, H, W, 1, P, 1, dilp)) return e;
+  if ((int64_t)B * H * W == 0) return PMT_OK;
+  if (C > 0 && corr1d_fwd_tc_ok(in1, in2, out, C, H, W, P, dilp, 3))
+    return launch_corr1d_fwd_tc(in1, in2, out, B, C, H, W, P, 3, static_cast<cudaStream_t>(stream));
+  return pmt_corr1d_fwd_simt_f32(in1, in2, out, B, C, H, W, P, dilp, stream);
+}
+
+int pmt_corr1d_bwd_f32(const float* in1, const float* in2, const float* gout, float* gin1, float* gin2,
+                       int B, int C, int H, int W, int P, int dilp, void* stream) {
+  if (int e = check_corr_args(in1, in2, gout, B, C, H, W, 1, P, 1, dilp)) return e;
+  PMT_CHECK_ARG(gin1 && gin2, "correlation backward: null gradient pointer");
+  if ((int64_t)B * C * H * W == 0) return PMT_OK;
+  if (corr1d_bwd_tc_ok(in1, in2, C, H, W, P, dilp, 3) && aligned16(gout))
+    return launch_corr1d_bwd_tc(in1, in2, gout, gin1, gin2, B, C, H, W, P, 3, static_cast<cudaStream_t>(stream));
+  return pmt_corr1d_bwd_simt_f32(in1, in2, gout, gin1, gin2, B, C, H, W, P, dilp, stream);
 }
 
 int pmt_corr1d_fwd_tc_f32(const float* in1, const float* in2, float* out, int B, int C, int H, int W, int P,
@@ -206,17 +239,6 @@ int pmt_corr1d_bwd_tc_f32(const float* in1, const float* in2, const float* gout,
     return PMT_ERR_UNSUPPORTED;
   }
   return launch_corr1d_bwd_tc(in1, in2, gout, gin1, gin2, B, C, H, W, P, passes, static_cast<cudaStream_t>(stream));
-}
-
-int pmt_corr1d_bwd_f32(const float* in1, const float* in2, const float* gout, float* gin1, float* gin2,
-                       int B, int C, int H, int W, int P, int dilp, void* stream) {
-  if (int e = check_corr_args(in1, in2, gout, B, C, H, W, 1, P, 1, dilp)) return e;
-  PMT_CHECK_ARG(gin1 && gin2, "correlation backward: null gradient pointer");
-  if ((int64_t)B * C * H * W == 0) return PMT_OK;
-  cudaStream_t st = static_cast<cudaStream_t>(stream);
-  if (corr1d_bwd_fast_ok(in1, in2, gout, C, W, P, dilp) && aligned16(gin1) && aligned16(gin2))
-    return launch_corr1d_bwd_tiled(in1, in2, gout, gin1, gin2, B, C, H, W, P, st);
-  return launch_corr_generic_bwd(in1, in2, gout, gin1, gin2, B, C, H, W, 1, P, 1, dilp, st);
 }
 
 int pmt_corr_fwd_f32(const float* in1, const float* in2, float* out, int B, int C, int H, int W, int pH,

@@ -33,31 +33,40 @@ def run_corr(pmt, L, R, G, patch, dil=1):
     return npy(out), npy(Ld.grad), npy(Rd.grad)
 
 
-# (B, C, H, W, P, expect_fast_path)
+# (B, C, H, W, P, engine the default entry points pick: 2 tensor core, 1 CUDA-core tiled, 0 generic)
 CORR1D_CASES = [
-    (2, 64, 64, 128, 40, True),     # BASELINE config 1
-    (2, 352, 32, 64, 17, True),     # production call inside minidsnetExt
-    (1, 64, 5, 512, 192, True),     # headline row shape
-    (1, 16, 3, 512, 193, True),     # largest P of the fast path
-    (1, 5, 3, 100, 8, True),        # ragged: W%64 != 0, C%16 != 0, even P
-    (2, 33, 2, 68, 7, True),        # C%32 == 1
-    (1, 3, 1, 4, 1, True),          # degenerate patch
-    (1, 7, 4, 260, 2, True),
-    (1, 40, 3, 132, 100, True),
-    (1, 4, 3, 62, 9, False),        # W%4 != 0 -> generic kernels
-    (1, 4, 3, 64, 250, False),      # P beyond the tiled band -> generic kernels
+    (2, 64, 64, 128, 40, 2),     # BASELINE config 1
+    (2, 352, 32, 64, 17, 1),     # production call inside minidsnetExt (C > 128: CUDA-core tiled backward)
+    (1, 64, 5, 512, 192, 2),     # headline row shape
+    (1, 16, 3, 512, 193, 2),     # largest P of the fast paths
+    (1, 5, 3, 100, 8, 2),        # ragged: W%64 != 0, C%16 != 0, even P
+    (2, 33, 2, 68, 7, 2),        # C%32 == 1
+    (1, 3, 1, 4, 1, 2),          # degenerate patch
+    (1, 7, 4, 260, 2, 2),
+    (1, 40, 3, 132, 100, 2),
+    (1, 128, 3, 960, 192, 2),    # config-4 row geometry (C=128, W=960)
+    (1, 4, 3, 62, 9, 0),         # W%4 != 0 -> generic kernels
+    (1, 4, 3, 64, 250, 0),       # P beyond the tiled band -> generic kernels
 ]
+TF32_TOL = 5e-3  # plain-TF32 tensor-core variant (north_star allows 2e-2 for the reduced-precision variant)
+
+
+@pytest.fixture(params=["auto", "simt"])
+def engine(request, pmt):
+    prev = pmt.set_correlation_engine(request.param)
+    yield request.param
+    pmt.set_correlation_engine(prev)
 
 
 @pytest.mark.parametrize("B,C,H,W,P,fast", CORR1D_CASES)
-def test_corr1d_vs_oracle(pmt, B, C, H, W, P, fast):
+def test_corr1d_vs_oracle(pmt, engine, B, C, H, W, P, fast):
     rng = np.random.default_rng(B * 1000 + C * 7 + W + P)
     L = rng.standard_normal((B, C, H, W), dtype=np.float32)
     R = rng.standard_normal((B, C, H, W), dtype=np.float32)
     G = rng.standard_normal((B, 1, P, H, W), dtype=np.float32)
     lib = pmt.load_library()
     t = torch.from_numpy(L).cuda()
-    assert lib.pmt_corr1d_uses_fast_path(vp(t), vp(t), vp(t), C, H, W, P, 1) == int(fast)
+    assert lib.pmt_corr1d_uses_fast_path(vp(t), vp(t), vp(t), C, H, W, P, 1) == fast
     out, g1, g2 = run_corr(pmt, L, R, G, (1, P))
     ref = oracle.corr_fwd(L, R, patch_size=(1, P))
     r1, r2 = oracle.corr_bwd(L, R, G, patch_size=(1, P))
@@ -72,6 +81,30 @@ def test_corr1d_vs_oracle(pmt, B, C, H, W, P, fast):
         w = np.arange(W)
         oob = (w + s < 0) | (w + s >= W)
         assert np.all(out[:, 0, p][..., oob] == 0.0)
+
+
+@pytest.mark.parametrize("B,C,H,W,P", [(2, 64, 64, 128, 40), (1, 64, 5, 512, 192), (1, 128, 3, 960, 192), (1, 5, 3, 100, 8)])
+def test_corr1d_tf32_variant(pmt, B, C, H, W, P):
+    """Reduced-precision tensor-core variant (plain TF32 inputs, fp32 accumulate) within its looser tolerance."""
+    rng = np.random.default_rng(P)
+    L = rng.standard_normal((B, C, H, W), dtype=np.float32)
+    R = rng.standard_normal((B, C, H, W), dtype=np.float32)
+    G = rng.standard_normal((B, 1, P, H, W), dtype=np.float32)
+    prev = pmt.set_correlation_engine("tf32")
+    try:
+        out, g1, g2 = run_corr(pmt, L, R, G, (1, P))
+    finally:
+        pmt.set_correlation_engine(prev)
+    r1, r2 = oracle.corr_bwd(L, R, G, patch_size=(1, P))
+    e = (rel_err(out, oracle.corr_fwd(L, R, patch_size=(1, P))), rel_err(g1, r1), rel_err(g2, r2))
+    assert max(e) <= TF32_TOL and min(e) > 1e-6   # really the TF32 engine, not the fp32 one
+    with pytest.raises(Exception):
+        prev = pmt.set_correlation_engine("tf32")
+        try:
+            bad = torch.zeros(1, 4, 3, 62, device="cuda:0")     # W % 4 != 0: no silent fallback
+            pmt.spatial_correlation_sample(bad, bad, patch_size=(1, 9))
+        finally:
+            pmt.set_correlation_engine(prev)
 
 
 @pytest.mark.parametrize("patch,dil", [((3, 5), 1), ((1, 5), 2), ((17, 17), 1), ((1, 21), 4), ((5, 1), (2, 1))])
@@ -117,7 +150,7 @@ def test_corr_kats(pmt):
     assert np.argwhere(out != 0).tolist() == [[0, 0, 4 + 19, 1, 10]]
 
 
-def test_corr_headline_shape_one_pair_vs_oracle(pmt):
+def test_corr_headline_shape_one_pair_vs_oracle(pmt, engine):
     """One full 256x512, C=64, P=192 pair against the C oracle (a few seconds of CPU)."""
     rng = np.random.default_rng(5)
     B, C, H, W, P = 1, 64, 256, 512, 192
@@ -130,7 +163,7 @@ def test_corr_headline_shape_one_pair_vs_oracle(pmt):
     assert rel_err(g1, r1) <= FP32_TOL and rel_err(g2, r2) <= FP32_TOL
 
 
-def test_corr_full_size_properties(pmt):
+def test_corr_full_size_properties(pmt, engine):
     """BASELINE sizes (B=4, C=64, 256x512, D=192): adjoint identity, linearity, determinism, all-ones count."""
     dev = torch.device("cuda:0")
     B, C, H, W, P = 4, 64, 256, 512, 192
