@@ -2,19 +2,20 @@
 // Both gradients are deterministic gathers (no atomics), one launch, blockIdx.y selects the gradient:
 //   mode 0: gin1[c,x] = sum_j Gd[x][j] * in2[c][x0+oo+j]        mode 1: gin2[c,x] = sum_j Gd[x][j] * in1[c][x0+oo+j]
 // where Gd[x][j] is the band matrix made of g (mode 0: g[j-delta-x][x]; mode 1: g[x+P-1+delta-j][x0+oo+j]).
-// Per CTA: 128 output columns x of one image row, all C channels (C <= 128):
+// A tile = 128 output columns x of one image row, all C channels (C <= 128):
 //   D[x (M=128 TMEM lanes)][c (N=C columns)] = sum over the band (K = 32*NKC columns, 320 for P=192).
-//   * B operand = the feature band: rows c, K contiguous along w -> K-major, fetched by TMA in
-//     32-column x C-channel boxes with the 128-byte swizzle, straight from NCHW;
-//   * A operand = Gd, K-major too, built on the fly from raw g staged by TMA (no global-load latency
-//     in the builders): mode 0 keeps the tile's [P][128] slice of g resident (32-row boxes, consumed as
-//     they land), mode 1 streams [160][32] blocks (one per K chunk, OOB rows/columns zero-filled by
-//     TMA); 8 builder warps re-lay them out shared->shared into the swizzled K-major stage with
-//     bank-conflict-free LDS/STS; for 3xTF32 they write hi and lo copies and also split the band;
-//   * warp 1 issues tcgen05.mma kind::tf32 (M=128, N=C, K=8), 4 k-steps per 32-column chunk; ring of
-//     stages with mbarriers (TMA -> builders -> MMA -> free);
-//   * epilogue: builder warps 0-3 read TMEM (tcgen05.ld) and store gin[c][x] rows directly -- a warp
-//     writes 32 consecutive columns of one channel per instruction (coalesced 128 bytes).
+// Persistent CTAs (one per SM, half of them per gradient) walk tiles with every stage of the pipeline
+// running ahead across tile boundaries:
+//   * warp 0 (TMA producer): the feature band = B operand (rows c, K contiguous along w -> K-major), one
+//     128-byte-swizzled [C][32] box per K chunk into a deep ring; raw g into a second ring -- mode 0: the
+//     tile's [P][128] slice as 32-row boxes (a box is recycled for the next tile as soon as its last
+//     chunk is built), mode 1: one [160][32] block per chunk (OOB rows/columns zero-filled by TMA);
+//   * warps 6-13 (builders): re-lay raw g out shared->shared into the swizzled K-major A operand Gd
+//     (bank-conflict-free LDS/STS); for 3xTF32 they write hi and lo copies and split the landed band;
+//   * warp 1 issues tcgen05.mma kind::tf32 (M=128, N=C, K=8; hi*hi + hi*lo + lo*hi for 3xTF32) into one
+//     of two TMEM accumulators and commits to the mbarriers that recycle the rings;
+//   * warps 2-5 (epilogue) drain the other accumulator with tcgen05.ld and store gin[c][x] directly:
+//     a warp writes 32 consecutive columns of one channel per instruction (coalesced 128 bytes).
 #include <stdlib.h>
 
 #include "tc_common.cuh"
@@ -22,35 +23,40 @@
 namespace pmt {
 namespace {
 
-constexpr int kTM = 128;         // output columns per CTA (UMMA M)
-constexpr int kKC = 32;          // band columns per ring stage (4 k-steps of 8)
-constexpr int kGdBytes = kTM * kKC * 4;  // 16 KB: A operand chunk
-constexpr int kBuilders = 8;     // builder warps
-constexpr int kThreads = 32 * (2 + kBuilders);
+constexpr int kTM = 128;                  // output columns per tile (UMMA M)
+constexpr int kKC = 32;                   // band columns per K chunk (4 k-steps of 8)
+constexpr int kGdBytes = kTM * kKC * 4;   // 16 KB: one A-operand chunk
+constexpr int kEpiWarps = 4;
+constexpr int kBuilders = 8;
+constexpr int kThreads = 32 * (2 + kEpiWarps + kBuilders);  // 448
+constexpr int kBox0Bytes = 32 * kTM * 4;          // mode 0: 32 rows of g x 128 columns (16 KB)
+constexpr int kRawRows1 = 160;                    // mode 1: rows of a raw block (>= 128+32-1)
+constexpr int kRawSlot1 = kRawRows1 * kKC * 4;    // 20 KB
+constexpr int kRawSlots1 = 4;
+constexpr int kMaxBandSlots = 8, kMaxGdSlots = 4;
 
 struct TcBwdMode {
   int oo;      // band column j <-> image column x0 + oo + j  (multiple of 4)
   int delta;
+  int koff;    // mode 0: box b of the g slice is last used by chunk min(NKC-1, b + koff)
 };
-
-constexpr int kRawRows1 = 160;                   // mode-1 raw block rows (>= 128+32-1)
-constexpr int kRawSlot1 = kRawRows1 * kKC * 4;   // 20 KB
 
 struct TcBwdArgs {
   int C, H, W, P, rW;
-  int raw_bytes;       // raw g staging region at the start of shared memory
-  int n_gboxes;        // mode 0: 32-row boxes of the resident g slice
-  int Cbox;            // channels rounded up to 16 (UMMA N)
-  int NKC;             // K chunks of 32 band columns
-  int n_xtiles;
-  int stages;
-  int stage_bytes, lo_off;
-  int bar_off;
+  int Cbox;            // channels rounded up to 32 (UMMA N, TMEM columns per accumulator)
+  int NKC;             // K chunks per tile
+  int n_xtiles, n_tiles;
+  int n_gboxes;        // mode 0: 32-row boxes of the resident g slice (= raw ring slots)
+  int gd_slots, band_slots;
+  int gd_slot_bytes, gd_lo_off;       // Gd ring slot: hi [16 KB] (+ lo [16 KB])
+  int band_slot_bytes, band_lo_off;   // band ring slot: hi [Cbox*128] (+ lo)
+  int gd_off, band_off, bar_off;      // byte offsets in dynamic shared memory (raw ring at 0)
   int tmem_cols;
   TcBwdMode m[2];
+  int debug;           // PMT_TC_DEBUG ablation bits: 4 skip Gd build, 32 skip band split, 16 skip MMA, 8 skip epilogue
 };
 
-// K-major, 128-byte swizzle: row r of a [rows][32 floats] chunk
+// K-major, 128-byte swizzle: element (row, col) of a [rows][32 floats] chunk
 __device__ __forceinline__ uint32_t kmajor_off(int row, int col) {
   return (uint32_t)((row >> 3) * 1024 + (row & 7) * 128 + ((((col >> 2) ^ (row & 7)) << 4) | ((col & 3) << 2)));
 }
@@ -62,20 +68,35 @@ __device__ __forceinline__ void split_tf32(float x, float& hi, float& lo) {
   lo = x - hi;
 }
 
+struct TileCoord {
+  int x0, h, n;
+};
+__device__ __forceinline__ TileCoord tile_coord(const TcBwdArgs& a, int i) {
+  const int t = blockIdx.x + i * gridDim.x;
+  TileCoord c;
+  c.x0 = (t % a.n_xtiles) * kTM;
+  c.h = (t / a.n_xtiles) % a.H;
+  c.n = t / (a.n_xtiles * a.H);
+  return c;
+}
+
 template <int kPasses>
 __global__ void __launch_bounds__(kThreads, 1)
 corr1d_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmIn1, const __grid_constant__ CUtensorMap tmIn2,
                      const __grid_constant__ CUtensorMap tmG0, const __grid_constant__ CUtensorMap tmG1,
                      float* __restrict__ gin1, float* __restrict__ gin2, const TcBwdArgs a) {
   extern __shared__ __align__(1024) unsigned char smem[];
-  uint64_t* full = reinterpret_cast<uint64_t*>(smem + a.bar_off);   // TMA band chunk landed
-  uint64_t* built = full + 8;                                        // builders finished the stage
-  uint64_t* empty = built + 8;                                       // MMAs finished reading the stage
-  uint64_t* raw_full = empty + 8;                                    // raw g box / block landed
-  uint64_t* raw_empty = raw_full + 8;                                // mode 1: builders done with a raw slot
-  uint64_t* tmem_full = raw_empty + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + 1);
-  unsigned char* stage0 = smem + a.raw_bytes;
+  uint64_t* band_full = reinterpret_cast<uint64_t*>(smem + a.bar_off);
+  uint64_t* band_empty = band_full + kMaxBandSlots;
+  uint64_t* gd_built = band_empty + kMaxBandSlots;
+  uint64_t* gd_empty = gd_built + kMaxGdSlots;
+  uint64_t* raw_full = gd_empty + kMaxGdSlots;
+  uint64_t* raw_empty = raw_full + 8;
+  uint64_t* tmem_full = raw_empty + 8;
+  uint64_t* tmem_empty = tmem_full + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+  unsigned char* gd_ring = smem + a.gd_off;
+  unsigned char* band_ring = smem + a.band_off;
 
   const int mode = blockIdx.y;
   const TcBwdMode m = a.m[mode];
@@ -83,23 +104,27 @@ corr1d_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmIn1, const __grid_con
   float* __restrict__ dst = mode == 0 ? gin1 : gin2;
 
   const int tid = threadIdx.x, wid = tid >> 5, lane = tid & 31;
-  int bid = blockIdx.x;
-  const int xt = bid % a.n_xtiles;
-  bid /= a.n_xtiles;
-  const int h = bid % a.H;
-  const int n = bid / a.H;
-  const int x0 = xt * kTM;
   const int band_bytes = a.Cbox * 128;
+  const int n_my = (a.n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;  // tiles of this CTA
+  const int G = n_my * a.NKC;                                                            // chunks of this CTA
 
   if (tid == 0) {
-    for (int s = 0; s < a.stages; ++s) {
-      mbar_init(&full[s], 1);
-      mbar_init(&built[s], kBuilders);
-      mbar_init(&empty[s], 1);
+    for (int s = 0; s < kMaxBandSlots; ++s) {
+      mbar_init(&band_full[s], 1);
+      mbar_init(&band_empty[s], 1);
     }
-    for (int s = 0; s < 8; ++s) mbar_init(&raw_full[s], 1);
-    for (int s = 0; s < 2; ++s) mbar_init(&raw_empty[s], kBuilders);
-    mbar_init(tmem_full, 1);
+    for (int s = 0; s < kMaxGdSlots; ++s) {
+      mbar_init(&gd_built[s], kBuilders);
+      mbar_init(&gd_empty[s], 1);
+    }
+    for (int s = 0; s < 8; ++s) {
+      mbar_init(&raw_full[s], 1);
+      mbar_init(&raw_empty[s], kBuilders);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&tmem_full[s], 1);
+      mbar_init(&tmem_empty[s], kEpiWarps);
+    }
     fence_mbar_init();
   }
   if (wid == 1) {
@@ -112,163 +137,211 @@ corr1d_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmIn1, const __grid_con
   const uint32_t tmem_base = *tmem_slot;
 
   if (wid == 0) {
-    // ===== TMA producer: raw g (resident boxes / streamed blocks) + one swizzled band box per stage =====
+    // ===== TMA producer: raw g runs kPre chunks ahead of the band, both rings span tile boundaries =====
     if (lane == 0) {
       tma_prefetch_desc(tmBand);
+      // Prefetch distance of the raw-g ring.  Mode 0: the slot of box k is released by the previous tile's
+      // chunk min(NKC-1, k+koff); that chunk must already have its band issued or the producer would wait on
+      // work it has not fed yet.  Mode 1: 4 slots, a slot is released by the chunk 4 positions earlier.
+      int kPre = 2;
       if (mode == 0) {
-        for (int b = 0; b < a.n_gboxes; ++b) {
-          mbar_arrive_expect_tx(&raw_full[b], 32u * kTM * 4u);
-          tma_load_4d(smem + b * (32 * kTM * 4), &tmG0, x0, h, 32 * b, n, &raw_full[b]);
-        }
+        const int ke = m.koff < a.NKC - 1 ? m.koff : a.NKC - 1;
+        kPre = a.NKC - ke - 1;
+        kPre = kPre < 0 ? 0 : (kPre > 3 ? 3 : kPre);
       }
-      for (int k = 0; k < a.NKC; ++k) {
-        if (mode == 1) {
-          const int slot = k & 1;
-          mbar_wait(&raw_empty[slot], ((uint32_t)(k >> 1) & 1u) ^ 1u);
-          mbar_arrive_expect_tx(&raw_full[slot], (uint32_t)kRawSlot1);
-          tma_load_4d(smem + slot * kRawSlot1, &tmG1, x0 + m.oo + kKC * k, h,
-                      a.P - 1 + m.delta - kKC * k - (kKC - 1), n, &raw_full[slot]);
+      for (int g = -kPre; g < G; ++g) {
+        const int gp = g + kPre;
+        if (gp < G) {
+          const int i = gp / a.NKC, k = gp - i * a.NKC;
+          const TileCoord tc_ = tile_coord(a, i);
+          if (mode == 0) {
+            if (k < a.n_gboxes) {
+              mbar_wait(&raw_empty[k], ((uint32_t)i & 1u) ^ 1u);  // previous tile is done with this box
+              mbar_arrive_expect_tx(&raw_full[k], (uint32_t)kBox0Bytes);
+              tma_load_4d(smem + k * kBox0Bytes, &tmG0, tc_.x0, tc_.h, 32 * k, tc_.n, &raw_full[k]);
+            }
+          } else {
+            const int slot = gp % kRawSlots1;
+            mbar_wait(&raw_empty[slot], ((uint32_t)(gp / kRawSlots1) & 1u) ^ 1u);
+            mbar_arrive_expect_tx(&raw_full[slot], (uint32_t)kRawSlot1);
+            tma_load_4d(smem + slot * kRawSlot1, &tmG1, tc_.x0 + m.oo + kKC * k, tc_.h,
+                        a.P - 1 + m.delta - kKC * k - (kKC - 1), tc_.n, &raw_full[slot]);
+          }
         }
-        const int st = k % a.stages;
-        const uint32_t ph = (uint32_t)(k / a.stages) & 1u;
-        mbar_wait(&empty[st], ph ^ 1u);
-        unsigned char* sb = stage0 + (size_t)st * a.stage_bytes + kGdBytes;
-        mbar_arrive_expect_tx(&full[st], (uint32_t)band_bytes);
-        tma_load_4d(sb, tmBand, x0 + m.oo + kKC * k, h, 0, n, &full[st]);
+        if (g >= 0) {
+          const int i = g / a.NKC, k = g - i * a.NKC;
+          const TileCoord tc_ = tile_coord(a, i);
+          const int bs = g % a.band_slots;
+          mbar_wait(&band_empty[bs], ((uint32_t)(g / a.band_slots) & 1u) ^ 1u);
+          mbar_arrive_expect_tx(&band_full[bs], (uint32_t)band_bytes);
+          tma_load_4d(band_ring + (size_t)bs * a.band_slot_bytes, tmBand, tc_.x0 + m.oo + kKC * k, tc_.h, 0, tc_.n,
+                      &band_full[bs]);
+        }
       }
     }
   } else if (wid == 1) {
     // ===== MMA issuer =====
     if (lane == 0) {
       const uint32_t idesc = tc::make_idesc(2, 0, 0, kTM, a.Cbox);
-      for (int k = 0; k < a.NKC; ++k) {
-        const int st = k % a.stages;
-        const uint32_t ph = (uint32_t)(k / a.stages) & 1u;
-        mbar_wait(&built[st], ph);
-        if (kPasses == 1) mbar_wait(&full[st], ph);  // 3x: the builders already waited for (and rewrote) the band
+      int g = 0;
+      for (int i = 0; i < n_my; ++i) {
+        const int buf = i & 1;
+        mbar_wait(&tmem_empty[buf], ((uint32_t)(i >> 1) & 1u) ^ 1u);  // epilogue drained this accumulator
         tc::fence_after_sync();
-        const uint32_t sa = smem_u32(stage0 + (size_t)st * a.stage_bytes);
-        const uint32_t sb = sa + kGdBytes;
+        const uint32_t d_tmem = tmem_base + (uint32_t)(buf * a.Cbox);
+        for (int k = 0; k < a.NKC; ++k, ++g) {
+          const int gs = g % a.gd_slots, bs = g % a.band_slots;
+          mbar_wait(&gd_built[gs], (uint32_t)(g / a.gd_slots) & 1u);
+          if (kPasses == 1) mbar_wait(&band_full[bs], (uint32_t)(g / a.band_slots) & 1u);
+          tc::fence_after_sync();
+          const uint32_t sa = smem_u32(gd_ring + (size_t)gs * a.gd_slot_bytes);
+          const uint32_t sb = smem_u32(band_ring + (size_t)bs * a.band_slot_bytes);
 #pragma unroll
-        for (int kk = 0; kk < kKC / 8; ++kk) {
-          const uint32_t acc = (k > 0 || kk > 0) ? 1u : 0u;
-          const uint64_t dA = tc::smem_desc(sa + kk * 32, 16, 1024, 2);
-          const uint64_t dB = tc::smem_desc(sb + kk * 32, 16, 1024, 2);
-          if (kPasses == 3) {
-            const uint64_t dAl = tc::smem_desc(sa + a.lo_off + kk * 32, 16, 1024, 2);
-            const uint64_t dBl = tc::smem_desc(sb + a.lo_off + kk * 32, 16, 1024, 2);
-            tc::mma_tf32(tmem_base, dAl, dB, idesc, acc);
-            tc::mma_tf32(tmem_base, dA, dBl, idesc, 1u);
-            tc::mma_tf32(tmem_base, dA, dB, idesc, 1u);
-          } else {
-            tc::mma_tf32(tmem_base, dA, dB, idesc, acc);
-          }
-        }
-        tc::mma_commit(&empty[st]);
-      }
-      tc::mma_commit(tmem_full);
-    }
-  } else {
-    // ===== builder warps =====
-    const int bw = wid - 2;  // 0..7
-    const int64_t pstride = (int64_t)a.H * a.W;
-    int boxes_ready = 0;
-    for (int k = 0; k < a.NKC; ++k) {
-      const int st = k % a.stages;
-      const uint32_t ph = (uint32_t)(k / a.stages) & 1u;
-      unsigned char* sa = stage0 + (size_t)st * a.stage_bytes;
-      if (mode == 0) {
-        // rows p <= 32k+31-delta are needed: boxes 0..k of the resident [P][128] slice
-        const int need = (k + 1 < a.n_gboxes) ? k + 1 : a.n_gboxes;
-        while (boxes_ready < need) mbar_wait(&raw_full[boxes_ready++], 0);
-        mbar_wait(&empty[st], ph ^ 1u);
-        const float* Gt = reinterpret_cast<const float*>(smem);
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const int it = bw + kBuilders * i;      // 32 warp tasks per chunk: (16-byte column c4, 32-row block xb)
-          const int c4 = it & 7, xb = it >> 3;
-          const int xl = 32 * xb + lane;
-          const int pb = kKC * k + 4 * c4 - m.delta - xl;  // p of column jj = 4*c4 + t is pb + t
-          float v[4];
-#pragma unroll
-          for (int t = 0; t < 4; ++t) {
-            const int p = pb + t;
-            v[t] = (p >= 0 && p < a.P) ? Gt[p * kTM + xl] : 0.f;
-          }
-          const uint32_t off = kmajor_off(xl, 4 * c4);
-          if (kPasses == 3) {
-            float4 hi, lo;
-            split_tf32(v[0], hi.x, lo.x);
-            split_tf32(v[1], hi.y, lo.y);
-            split_tf32(v[2], hi.z, lo.z);
-            split_tf32(v[3], hi.w, lo.w);
-            *reinterpret_cast<float4*>(sa + off) = hi;
-            *reinterpret_cast<float4*>(sa + a.lo_off + off) = lo;
-          } else {
-            *reinterpret_cast<float4*>(sa + off) = make_float4(v[0], v[1], v[2], v[3]);
-          }
-        }
-      } else {
-        const int slot = k & 1;
-        mbar_wait(&raw_full[slot], (uint32_t)(k >> 1) & 1u);
-        mbar_wait(&empty[st], ph ^ 1u);
-        const float* raw = reinterpret_cast<const float*>(smem + slot * kRawSlot1);
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const int r = bw + kBuilders * i;       // 32 warp tasks per chunk: 4 rows x 32 columns (lane = column)
-#pragma unroll
-          for (int t = 0; t < 4; ++t) {
-            const int xl = 4 * r + t;
-            const float v = raw[(xl + 31 - lane) * kKC + lane];   // g[p_first + xl + 31 - jj][column jj]
-            const uint32_t off = kmajor_off(xl, lane);
+          for (int kk = 0; kk < kKC / 8; ++kk) {
+            if (a.debug & 16) break;
+            const uint32_t acc = (k > 0 || kk > 0) ? 1u : 0u;
+            const uint64_t dA = tc::smem_desc(sa + kk * 32, 16, 1024, 2);
+            const uint64_t dB = tc::smem_desc(sb + kk * 32, 16, 1024, 2);
             if (kPasses == 3) {
-              float hi, lo;
-              split_tf32(v, hi, lo);
-              *reinterpret_cast<float*>(sa + off) = hi;
-              *reinterpret_cast<float*>(sa + a.lo_off + off) = lo;
+              const uint64_t dAl = tc::smem_desc(sa + a.gd_lo_off + kk * 32, 16, 1024, 2);
+              const uint64_t dBl = tc::smem_desc(sb + a.band_lo_off + kk * 32, 16, 1024, 2);
+              tc::mma_tf32(d_tmem, dAl, dB, idesc, acc);
+              tc::mma_tf32(d_tmem, dA, dBl, idesc, 1u);
+              tc::mma_tf32(d_tmem, dA, dB, idesc, 1u);
             } else {
-              *reinterpret_cast<float*>(sa + off) = v;
+              tc::mma_tf32(d_tmem, dA, dB, idesc, acc);
             }
           }
+          tc::mma_commit(&gd_empty[gs]);
+          tc::mma_commit(&band_empty[bs]);
         }
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&raw_empty[slot]);
+        tc::mma_commit(&tmem_full[buf]);
       }
-      if (kPasses == 3) {
-        // split the landed feature band chunk into hi / lo (position-wise, layout agnostic)
-        mbar_wait(&full[st], ph);
-        unsigned char* sb = sa + kGdBytes;
-        const int nch = band_bytes / 16;
-        for (int c = (bw * 32 + lane); c < nch; c += kBuilders * 32) {
-          float4* q = reinterpret_cast<float4*>(sb + 16 * c);
-          const float4 x = *q;
-          float4 hi, lo;
-          split_tf32(x.x, hi.x, lo.x);
-          split_tf32(x.y, hi.y, lo.y);
-          split_tf32(x.z, hi.z, lo.z);
-          split_tf32(x.w, hi.w, lo.w);
-          *q = hi;
-          *reinterpret_cast<float4*>(sb + a.lo_off + 16 * c) = lo;
-        }
-      }
-      fence_proxy_async();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&built[st]);
     }
-    // ===== epilogue (builder warps 0..3): TMEM -> coalesced global stores =====
-    if (bw < 4) {
-      const int q = wid & 3;
-      const int xl = 32 * q + lane;
-      mbar_wait(tmem_full, 0);
+  } else if (wid < 2 + kEpiWarps) {
+    // ===== epilogue: TMEM -> coalesced global stores =====
+    const int q = wid & 3;
+    const int xl = 32 * q + lane;
+    const int64_t pstride = (int64_t)a.H * a.W;
+    for (int i = 0; i < n_my; ++i) {
+      const int buf = i & 1;
+      const TileCoord tc_ = tile_coord(a, i);
+      mbar_wait(&tmem_full[buf], (uint32_t)(i >> 1) & 1u);
       tc::fence_after_sync();
-      const bool ok = x0 + xl < a.W;
-      float* o = dst + ((int64_t)n * a.C * a.H + h) * (int64_t)a.W + x0 + xl;
-      for (int cb = 0; cb < a.Cbox; cb += 32) {
+      const bool ok = tc_.x0 + xl < a.W;
+      float* o = dst + ((int64_t)tc_.n * a.C * a.H + tc_.h) * (int64_t)a.W + tc_.x0 + xl;
+      for (int cb = 0; cb < a.Cbox && !(a.debug & 8); cb += 32) {
         float v[32];
-        tc::tmem_ld32(tmem_base + ((uint32_t)(32 * q) << 16) + (uint32_t)cb, v);
+        tc::tmem_ld32(tmem_base + ((uint32_t)(32 * q) << 16) + (uint32_t)(buf * a.Cbox + cb), v);
 #pragma unroll
         for (int cc = 0; cc < 32; ++cc)
           if (ok && cb + cc < a.C) o[(int64_t)(cb + cc) * pstride] = v[cc];
+      }
+      tc::fence_before_sync();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tmem_empty[buf]);
+    }
+  } else {
+    // ===== builder warps =====
+    const int bw = wid - 2 - kEpiWarps;  // 0..7
+    int g = 0;
+    for (int i = 0; i < n_my; ++i) {
+      int boxes_ready = 0;
+      for (int k = 0; k < a.NKC; ++k, ++g) {
+        const int gs = g % a.gd_slots;
+        unsigned char* sa = gd_ring + (size_t)gs * a.gd_slot_bytes;
+        if (mode == 0) {
+          // rows p <= 32k+31-delta are needed: boxes 0..k of this tile's [P][128] slice
+          const int need = (k + 1 < a.n_gboxes) ? k + 1 : a.n_gboxes;
+          while (boxes_ready < need) mbar_wait(&raw_full[boxes_ready++], (uint32_t)i & 1u);
+          mbar_wait(&gd_empty[gs], ((uint32_t)(g / a.gd_slots) & 1u) ^ 1u);
+          const float* Gt = reinterpret_cast<const float*>(smem);
+#pragma unroll
+          for (int it = 0; it < 4; ++it) {
+            if (a.debug & 4) break;
+            const int task = bw + kBuilders * it;   // 32 warp tasks per chunk: (16-byte column c4, 32-row block xb)
+            const int c4 = task & 7, xb = task >> 3;
+            const int xl = 32 * xb + lane;
+            const int pb = kKC * k + 4 * c4 - m.delta - xl;  // p of column jj = 4*c4 + t is pb + t
+            float v[4];
+#pragma unroll
+            for (int t = 0; t < 4; ++t) {
+              const int p = pb + t;
+              v[t] = (p >= 0 && p < a.P) ? Gt[p * kTM + xl] : 0.f;
+            }
+            const uint32_t off = kmajor_off(xl, 4 * c4);
+            if (kPasses == 3) {
+              float4 hi, lo;
+              split_tf32(v[0], hi.x, lo.x);
+              split_tf32(v[1], hi.y, lo.y);
+              split_tf32(v[2], hi.z, lo.z);
+              split_tf32(v[3], hi.w, lo.w);
+              *reinterpret_cast<float4*>(sa + off) = hi;
+              *reinterpret_cast<float4*>(sa + a.gd_lo_off + off) = lo;
+            } else {
+              *reinterpret_cast<float4*>(sa + off) = make_float4(v[0], v[1], v[2], v[3]);
+            }
+          }
+          // recycle the boxes whose last reader was this chunk (the next tile's loads may land in them)
+          __syncwarp();
+          if (lane == 0) {
+            if (k < a.NKC - 1) {
+              const int b = k - m.koff;
+              if (b >= 0 && b < a.n_gboxes) mbar_arrive(&raw_empty[b]);
+            } else {
+              int b = a.NKC - 1 - m.koff;
+              if (b < 0) b = 0;
+              for (; b < a.n_gboxes; ++b) mbar_arrive(&raw_empty[b]);
+            }
+          }
+        } else {
+          const int slot = g % kRawSlots1;
+          mbar_wait(&raw_full[slot], (uint32_t)(g / kRawSlots1) & 1u);
+          mbar_wait(&gd_empty[gs], ((uint32_t)(g / a.gd_slots) & 1u) ^ 1u);
+          const float* raw = reinterpret_cast<const float*>(smem + slot * kRawSlot1);
+#pragma unroll
+          for (int it = 0; it < 4; ++it) {
+            if (a.debug & 4) break;
+            const int r = bw + kBuilders * it;      // 32 warp tasks per chunk: 4 rows x 32 columns (lane = column)
+#pragma unroll
+            for (int t = 0; t < 4; ++t) {
+              const int xl = 4 * r + t;
+              const float v = raw[(xl + 31 - lane) * kKC + lane];   // g[p_first + xl + 31 - jj][column jj]
+              const uint32_t off = kmajor_off(xl, lane);
+              if (kPasses == 3) {
+                float hi, lo;
+                split_tf32(v, hi, lo);
+                *reinterpret_cast<float*>(sa + off) = hi;
+                *reinterpret_cast<float*>(sa + a.gd_lo_off + off) = lo;
+              } else {
+                *reinterpret_cast<float*>(sa + off) = v;
+              }
+            }
+          }
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&raw_empty[slot]);
+        }
+        if (kPasses == 3) {
+          // split the landed feature band chunk into hi / lo (position-wise, layout agnostic)
+          const int bs = g % a.band_slots;
+          mbar_wait(&band_full[bs], (uint32_t)(g / a.band_slots) & 1u);
+          unsigned char* sb = band_ring + (size_t)bs * a.band_slot_bytes;
+          const int nch = band_bytes / 16;
+          for (int c = (bw * 32 + lane); c < nch && !(a.debug & 32); c += kBuilders * 32) {
+            float4* q = reinterpret_cast<float4*>(sb + 16 * c);
+            const float4 x = *q;
+            float4 hi, lo;
+            split_tf32(x.x, hi.x, lo.x);
+            split_tf32(x.y, hi.y, lo.y);
+            split_tf32(x.z, hi.z, lo.z);
+            split_tf32(x.w, hi.w, lo.w);
+            *q = hi;
+            *reinterpret_cast<float4*>(sb + a.band_lo_off + 16 * c) = lo;
+          }
+        }
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&gd_built[gs]);
       }
     }
   }
@@ -290,25 +363,35 @@ int fill_args(TcBwdArgs* a, int C, int H, int W, int P, int passes) {
   a->m[0].oo = oo0 - a->m[0].delta;
   a->m[1].delta = ((oo1 % 4) + 4) % 4;
   a->m[1].oo = oo1 - a->m[1].delta;
+  a->m[0].koff = (kTM + kKC - 2 + a->m[0].delta) / kKC;
+  a->m[1].koff = 0;
   const int dmax = a->m[0].delta > a->m[1].delta ? a->m[0].delta : a->m[1].delta;
   a->NKC = ceil_div(kTM + P - 1 + dmax, kKC);
   a->n_xtiles = ceil_div(W, kTM);
-  const int hi_bytes = kGdBytes + a->Cbox * 128;
-  a->lo_off = hi_bytes;
-  a->stage_bytes = hi_bytes * (passes == 3 ? 2 : 1);
+  a->n_tiles = 0;  // set by the launcher (needs B)
   a->n_gboxes = ceil_div(P, 32);
   if (a->n_gboxes > 8) return 1;
-  const int raw0 = a->n_gboxes * 32 * kTM * 4, raw1 = 2 * kRawSlot1;
-  a->raw_bytes = round_up(raw0 > raw1 ? raw0 : raw1, 1024);
-  int stages = (227 * 1024 - 512 - a->raw_bytes) / a->stage_bytes;
-  if (stages > 6) stages = 6;
-  if (stages > a->NKC) stages = a->NKC;
-  if (stages < 2) return 1;
-  a->stages = stages;
-  a->bar_off = a->raw_bytes + stages * a->stage_bytes;
+  const int raw0 = a->n_gboxes * kBox0Bytes, raw1 = kRawSlots1 * kRawSlot1;
+  const int raw_bytes = round_up(raw0 > raw1 ? raw0 : raw1, 1024);
+  const int mult = passes == 3 ? 2 : 1;
+  a->gd_lo_off = kGdBytes;
+  a->gd_slot_bytes = kGdBytes * mult;
+  a->band_lo_off = a->Cbox * 128;
+  a->band_slot_bytes = a->Cbox * 128 * mult;
+  a->gd_slots = passes == 3 ? 2 : 3;
+  const int left = 227 * 1024 - 1024 - raw_bytes - a->gd_slots * a->gd_slot_bytes;
+  int bslots = left / a->band_slot_bytes;
+  if (bslots > kMaxBandSlots) bslots = kMaxBandSlots;
+  if (bslots < 2) return 1;
+  a->band_slots = bslots;
+  a->gd_off = raw_bytes;
+  a->band_off = a->gd_off + a->gd_slots * a->gd_slot_bytes;
+  a->bar_off = a->band_off + a->band_slots * a->band_slot_bytes;
   int cols = 32;
-  while (cols < a->Cbox) cols *= 2;
+  while (cols < 2 * a->Cbox) cols *= 2;
   a->tmem_cols = cols;
+  const char* dbg = getenv("PMT_TC_DEBUG");
+  a->debug = dbg ? atoi(dbg) : 0;
   return 0;
 }
 
@@ -330,9 +413,13 @@ int launch_corr1d_bwd_tc(const float* in1, const float* in2, const float* gout, 
   if (int e = make_tmap_nchw_ex(&tm2, in2, B, C, H, W, kKC, a.Cbox, 1)) return e;
   if (int e = make_tmap_nchw_ex(&tmG0, gout, B, P, H, W, kTM, 32, 0)) return e;
   if (int e = make_tmap_nchw_ex(&tmG1, gout, B, P, H, W, kKC, kRawRows1, 0)) return e;
-  const int smem_bytes = a.bar_off + 512;
-  const int64_t gx = (int64_t)B * H * a.n_xtiles;
-  PMT_CHECK_ARG(gx < (1ll << 31), "corr1d tc bwd: grid too large");
+  const int smem_bytes = a.bar_off + 1024;
+  const int64_t tiles = (int64_t)B * H * a.n_xtiles;
+  PMT_CHECK_ARG(tiles < (1ll << 31), "corr1d tc bwd: too many tiles");
+  a.n_tiles = (int)tiles;
+  int per_mode = sm_count() / 2;  // persistent: one CTA per SM, half of the SMs per gradient
+  if (per_mode < 1) per_mode = 1;
+  const int64_t gx = tiles < per_mode ? tiles : per_mode;
   if (passes == 3) {
     PMT_CUDA_OK(cudaFuncSetAttribute(corr1d_bwd_tc_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
     corr1d_bwd_tc_kernel<3><<<dim3((unsigned)gx, 2), kThreads, smem_bytes, st>>>(tm1, tm2, tmG0, tmG1, gin1, gin2, a);

@@ -32,7 +32,7 @@ struct TcFwdArgs {
   int NB;                // band boxes of 32 columns
   int N1, N2;            // MMA N of the two band halves (N2 may be 0)
   int tmem_cols;         // power of two >= 32*NB
-  int n_wtiles, n_cchunks;
+  int n_wtiles, n_cchunks, n_tiles;
   int stages;
   int stage_bytes;       // (4+NB)*kBoxBytes * (hi+lo ? 2 : 1)
   int lo_off;            // byte offset of the lo copy inside a stage
@@ -56,15 +56,10 @@ corr1d_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmL, const __grid_const
   uint64_t* empty = full + 8;
   uint64_t* xf_done = empty + 8;
   uint64_t* tmem_full = xf_done + 8;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + 1);
+  uint64_t* tmem_empty = tmem_full + 1;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 1);
 
   const int tid = threadIdx.x, wid = tid >> 5, lane = tid & 31;
-  int bid = blockIdx.x;
-  const int wt = bid % a.n_wtiles;
-  bid /= a.n_wtiles;
-  const int h = bid % a.H;
-  const int n = bid / a.H;
-  const int w0 = wt * kTM;
   const int nboxes = kLBlocks + a.NB;
 
   if (tid == 0) {
@@ -74,6 +69,7 @@ corr1d_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmL, const __grid_const
       mbar_init(&xf_done[s], 4);
     }
     mbar_init(tmem_full, 1);
+    mbar_init(tmem_empty, 4);
     fence_mbar_init();
   }
   if (wid == 1) {
@@ -85,6 +81,8 @@ corr1d_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmL, const __grid_const
   tc::fence_after_sync();
   const uint32_t tmem_base = *tmem_slot;
 
+  // Persistent CTA: tiles blockIdx.x, blockIdx.x + gridDim.x, ...  Every role walks the same tile list and the
+  // same global chunk counter g, so the smem ring keeps streaming across tile boundaries.
   if (wid == 0) {
     // ===== TMA producer =====
     if (lane == 0) {
@@ -92,19 +90,24 @@ corr1d_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmL, const __grid_const
       tma_prefetch_desc(&tmR);
     }
     const uint32_t bytes = (uint32_t)nboxes * kBoxBytes;
-    for (int k = 0; k < a.n_cchunks; ++k) {
-      const int st = k % a.stages;
-      const uint32_t ph = (uint32_t)(k / a.stages) & 1u;
-      mbar_wait(&empty[st], ph ^ 1u);
-      unsigned char* sbase = smem + (size_t)st * a.stage_bytes;
-      if (lane == 0) mbar_arrive_expect_tx(&full[st], bytes);
-      __syncwarp();
-      if (lane < nboxes) {
-        if (lane < kLBlocks)
-          tma_load_4d(sbase + lane * kBoxBytes, &tmL, w0 + 32 * lane, h, k * kCK, n, &full[st]);
-        else
-          tma_load_4d(sbase + lane * kBoxBytes, &tmR, w0 - a.rW - a.delta + 32 * (lane - kLBlocks), h, k * kCK, n,
-                      &full[st]);
+    int g = 0;
+    for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x) {
+      const int wt = tile % a.n_wtiles, h = (tile / a.n_wtiles) % a.H, n = tile / (a.n_wtiles * a.H);
+      const int w0 = wt * kTM;
+      for (int k = 0; k < a.n_cchunks; ++k, ++g) {
+        const int st = g % a.stages;
+        const uint32_t ph = (uint32_t)(g / a.stages) & 1u;
+        mbar_wait(&empty[st], ph ^ 1u);
+        unsigned char* sbase = smem + (size_t)st * a.stage_bytes;
+        if (lane == 0) mbar_arrive_expect_tx(&full[st], bytes);
+        __syncwarp();
+        if (lane < nboxes) {
+          if (lane < kLBlocks)
+            tma_load_4d(sbase + lane * kBoxBytes, &tmL, w0 + 32 * lane, h, k * kCK, n, &full[st]);
+          else
+            tma_load_4d(sbase + lane * kBoxBytes, &tmR, w0 - a.rW - a.delta + 32 * (lane - kLBlocks), h, k * kCK, n,
+                        &full[st]);
+        }
       }
     }
   } else if (wid == 1) {
@@ -113,105 +116,112 @@ corr1d_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmL, const __grid_const
       const uint32_t idesc1 = tc::make_idesc(2, 1, 1, kTM, a.N1);
       const uint32_t idesc2 = tc::make_idesc(2, 1, 1, kTM, a.N2 > 0 ? a.N2 : 16);
       const int nb1 = a.N1 / 32;
-      for (int k = 0; k < a.n_cchunks; ++k) {
-        const int st = k % a.stages;
-        const uint32_t ph = (uint32_t)(k / a.stages) & 1u;
-        mbar_wait(kPasses == 3 ? &xf_done[st] : &full[st], ph);
+      int g = 0, it = 0;
+      for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x, ++it) {
+        mbar_wait(tmem_empty, ((uint32_t)it & 1u) ^ 1u);  // epilogue of the previous tile has drained TMEM
         tc::fence_after_sync();
-        const uint32_t sbase = smem_u32(smem + (size_t)st * a.stage_bytes);
+        for (int k = 0; k < a.n_cchunks; ++k, ++g) {
+          const int st = g % a.stages;
+          const uint32_t ph = (uint32_t)(g / a.stages) & 1u;
+          mbar_wait(kPasses == 3 ? &xf_done[st] : &full[st], ph);
+          tc::fence_after_sync();
+          const uint32_t sbase = smem_u32(smem + (size_t)st * a.stage_bytes);
 #pragma unroll
-        for (int kk = 0; kk < kCK / 8; ++kk) {
-          const uint32_t acc = (k > 0 || kk > 0) ? 1u : 0u;
-          const uint32_t a_hi = sbase + kk * 1024;
-          const uint32_t b1_hi = sbase + kLBlocks * kBoxBytes + kk * 1024;
-          const uint32_t b2_hi = b1_hi + nb1 * kBoxBytes;
-          const uint64_t dA = mn_desc(a_hi, kBoxBytes, 1024);
-          const uint64_t dB1 = mn_desc(b1_hi, kBoxBytes, 1024);
-          const uint64_t dB2 = mn_desc(b2_hi, kBoxBytes, 1024);
-          if (kPasses == 3) {
-            const uint64_t dAl = mn_desc(a_hi + a.lo_off, kBoxBytes, 1024);
-            const uint64_t dB1l = mn_desc(b1_hi + a.lo_off, kBoxBytes, 1024);
-            const uint64_t dB2l = mn_desc(b2_hi + a.lo_off, kBoxBytes, 1024);
-            // small cross terms first, then the dominant hi*hi term
-            tc::mma_tf32(tmem_base, dAl, dB1, idesc1, acc);
-            tc::mma_tf32(tmem_base, dA, dB1l, idesc1, 1u);
-            tc::mma_tf32(tmem_base, dA, dB1, idesc1, 1u);
-            if (a.N2 > 0) {
-              tc::mma_tf32(tmem_base + a.N1, dAl, dB2, idesc2, acc);
-              tc::mma_tf32(tmem_base + a.N1, dA, dB2l, idesc2, 1u);
-              tc::mma_tf32(tmem_base + a.N1, dA, dB2, idesc2, 1u);
+          for (int kk = 0; kk < kCK / 8 && !(a.debug & 16); ++kk) {
+            const uint32_t acc = (k > 0 || kk > 0) ? 1u : 0u;
+            const uint32_t a_hi = sbase + kk * 1024;
+            const uint32_t b1_hi = sbase + kLBlocks * kBoxBytes + kk * 1024;
+            const uint32_t b2_hi = b1_hi + nb1 * kBoxBytes;
+            const uint64_t dA = mn_desc(a_hi, kBoxBytes, 1024);
+            const uint64_t dB1 = mn_desc(b1_hi, kBoxBytes, 1024);
+            const uint64_t dB2 = mn_desc(b2_hi, kBoxBytes, 1024);
+            if (kPasses == 3) {
+              const uint64_t dAl = mn_desc(a_hi + a.lo_off, kBoxBytes, 1024);
+              const uint64_t dB1l = mn_desc(b1_hi + a.lo_off, kBoxBytes, 1024);
+              const uint64_t dB2l = mn_desc(b2_hi + a.lo_off, kBoxBytes, 1024);
+              // small cross terms first, then the dominant hi*hi term
+              tc::mma_tf32(tmem_base, dAl, dB1, idesc1, acc);
+              tc::mma_tf32(tmem_base, dA, dB1l, idesc1, 1u);
+              tc::mma_tf32(tmem_base, dA, dB1, idesc1, 1u);
+              if (a.N2 > 0) {
+                tc::mma_tf32(tmem_base + a.N1, dAl, dB2, idesc2, acc);
+                tc::mma_tf32(tmem_base + a.N1, dA, dB2l, idesc2, 1u);
+                tc::mma_tf32(tmem_base + a.N1, dA, dB2, idesc2, 1u);
+              }
+            } else {
+              tc::mma_tf32(tmem_base, dA, dB1, idesc1, acc);
+              if (a.N2 > 0) tc::mma_tf32(tmem_base + a.N1, dA, dB2, idesc2, acc);
             }
-          } else {
-            tc::mma_tf32(tmem_base, dA, dB1, idesc1, acc);
-            if (a.N2 > 0) tc::mma_tf32(tmem_base + a.N1, dA, dB2, idesc2, acc);
           }
+          tc::mma_commit(&empty[st]);  // ring slot reusable once these MMAs have read it
         }
-        tc::mma_commit(&empty[st]);  // ring slot reusable once these MMAs have read it
+        tc::mma_commit(tmem_full);     // accumulator of this tile complete
       }
-      tc::mma_commit(tmem_full);     // accumulator complete
     }
   } else if (wid < 6) {
     // ===== epilogue warps: TMEM -> registers -> un-skewed staging tile -> TMA store =====
     const int q = wid & 3;               // TMEM lane quarter this warp may access
     const int wl = 32 * q + lane;        // output column within the tile (= TMEM lane)
-    float* tile = reinterpret_cast<float*>(smem + a.tile_off);
-    mbar_wait(tmem_full, 0);
-    tc::fence_after_sync();
+    float* tile_s = reinterpret_cast<float*>(smem + a.tile_off);
     const int c_lo = (32 * q + a.delta) / 32;
     int c_hi = (32 * q + 31 + a.delta + a.P - 1) / 32;
     if (c_hi > a.NB - 1) c_hi = a.NB - 1;
-    for (int cb = c_lo; cb <= c_hi; ++cb) {
-      float v[32];
-      if (a.debug == 2) {
-        // write a lane/column pattern with tcgen05.st, then read it back
-        for (int jj = 0; jj < 32; ++jj) {
-          const uint32_t val = __float_as_uint((float)(wl * 1000 + 32 * cb + jj));
-          asm volatile("tcgen05.st.sync.aligned.32x32b.x1.b32 [%0], {%1};" ::"r"(tmem_base + ((uint32_t)(32 * q) << 16) + (uint32_t)(32 * cb + jj)), "r"(val) : "memory");
-        }
-        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
-      }
-      tc::tmem_ld32(tmem_base + ((uint32_t)(32 * q) << 16) + (uint32_t)(32 * cb), v);
-      if (a.debug == 1) {
-        for (int jj = 0; jj < 32; ++jj) v[jj] = (float)(wl * 1000 + 32 * cb + jj);
-      }
-      const int pbase = 32 * cb - a.delta - wl;  // p of column jj is pbase + jj
+    int it = 0;
+    for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x, ++it) {
+      const int wt = tile % a.n_wtiles, h = (tile / a.n_wtiles) % a.H, n = tile / (a.n_wtiles * a.H);
+      mbar_wait(tmem_full, (uint32_t)it & 1u);
+      tc::fence_after_sync();
+      if (wid == 2 && lane == 0) tc::tma_store_wait_read<0>();  // previous tile's store has read the staging tile
+      named_bar_sync(1, 128);
+      for (int cb = c_lo; cb <= c_hi && !(a.debug & 8); ++cb) {
+        float v[32];
+        tc::tmem_ld32(tmem_base + ((uint32_t)(32 * q) << 16) + (uint32_t)(32 * cb), v);
+        const int pbase = 32 * cb - a.delta - wl;  // p of column jj is pbase + jj
 #pragma unroll
-      for (int jj = 0; jj < 32; ++jj) {
-        const int p = pbase + jj;
-        if (p >= 0 && p < a.P) tile[p * kTM + wl] = v[jj];
+        for (int jj = 0; jj < 32; ++jj) {
+          const int p = pbase + jj;
+          if (p >= 0 && p < a.P) tile_s[p * kTM + wl] = v[jj];
+        }
+      }
+      tc::fence_before_sync();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tmem_empty);  // this warp's TMEM reads are done: the next tile's MMAs may start
+      fence_proxy_async();                     // generic-proxy writes -> visible to the TMA store
+      named_bar_sync(1, 128);
+      if (wid == 2 && lane == 0) {
+        tc::tma_store_4d(&tmO, tile_s, wt * kTM, h, 0, n);
+        tc::tma_store_commit();
       }
     }
-    fence_proxy_async();           // generic-proxy writes -> visible to the TMA store
-    named_bar_sync(1, 128);
-    if (wid == 2 && lane == 0) {
-      tc::tma_store_4d(&tmO, tile, w0, h, 0, n);
-      tc::tma_store_commit();
-      tc::tma_store_wait_read<0>();
-    }
+    if (wid == 2 && lane == 0) tc::tma_store_wait<0>();
   } else {
     // ===== transform warps (kPasses == 3): split staged fp32 into tf32 hi + lo =====
     const int t = tid - 6 * 32;  // 0..127
     const int nchunks = nboxes * (kBoxBytes / 16);
-    for (int k = 0; k < a.n_cchunks; ++k) {
-      const int st = k % a.stages;
-      const uint32_t ph = (uint32_t)(k / a.stages) & 1u;
-      mbar_wait(&full[st], ph);
-      unsigned char* sbase = smem + (size_t)st * a.stage_bytes;
-      for (int c = t; c < nchunks; c += 128) {
-        float4* p = reinterpret_cast<float4*>(sbase + 16 * c);
-        const float4 x = *p;
-        float4 hi, lo;
-        uint32_t u;
-        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x.x)); hi.x = __uint_as_float(u); lo.x = x.x - hi.x;
-        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x.y)); hi.y = __uint_as_float(u); lo.y = x.y - hi.y;
-        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x.z)); hi.z = __uint_as_float(u); lo.z = x.z - hi.z;
-        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x.w)); hi.w = __uint_as_float(u); lo.w = x.w - hi.w;
-        *p = hi;
-        *reinterpret_cast<float4*>(sbase + a.lo_off + 16 * c) = lo;
+    int g = 0;
+    for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x) {
+      for (int k = 0; k < a.n_cchunks; ++k, ++g) {
+        const int st = g % a.stages;
+        const uint32_t ph = (uint32_t)(g / a.stages) & 1u;
+        mbar_wait(&full[st], ph);
+        unsigned char* sbase = smem + (size_t)st * a.stage_bytes;
+#pragma unroll 2
+        for (int c = t; c < nchunks && !(a.debug & 4); c += 128) {
+          float4* p = reinterpret_cast<float4*>(sbase + 16 * c);
+          const float4 x = *p;
+          float4 hi, lo;
+          uint32_t u;
+          asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x.x)); hi.x = __uint_as_float(u); lo.x = x.x - hi.x;
+          asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x.y)); hi.y = __uint_as_float(u); lo.y = x.y - hi.y;
+          asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x.z)); hi.z = __uint_as_float(u); lo.z = x.z - hi.z;
+          asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x.w)); hi.w = __uint_as_float(u); lo.w = x.w - hi.w;
+          *p = hi;
+          *reinterpret_cast<float4*>(sbase + a.lo_off + 16 * c) = lo;
+        }
+        fence_proxy_async();  // make the rewritten stage visible to the tensor core's async-proxy reads
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&xf_done[st]);
       }
-      fence_proxy_async();  // make the rewritten stage visible to the tensor core's async-proxy reads
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&xf_done[st]);
     }
   }
 
@@ -236,6 +246,7 @@ int fill_args(TcFwdArgs* a, int C, int H, int W, int P, int passes) {
   a->tmem_cols = cols;
   a->n_wtiles = ceil_div(W, kTM);
   a->n_cchunks = ceil_div(C, kCK);
+  a->n_tiles = 0;  // set by the launcher (needs B)
   const int hi_bytes = (kLBlocks + a->NB) * kBoxBytes;
   a->lo_off = hi_bytes;
   a->stage_bytes = hi_bytes * (passes == 3 ? 2 : 1);
@@ -243,7 +254,6 @@ int fill_args(TcFwdArgs* a, int C, int H, int W, int P, int passes) {
   const int budget = 227 * 1024 - 512 - tile_bytes;
   int stages = budget / a->stage_bytes;
   if (stages > 8) stages = 8;
-  if (stages > a->n_cchunks) stages = a->n_cchunks;
   if (stages < 1) return 1;
   a->stages = stages;
   a->tile_off = stages * a->stage_bytes;
@@ -277,8 +287,10 @@ int launch_corr1d_fwd_tc(const float* in1, const float* in2, float* out, int B, 
   if (int e = make_tmap_nchw_ex(&tmR, in2, B, C, H, W, 32, kCK, 2)) return e;
   if (int e = make_tmap_nchw_ex(&tmO, out, B, P, H, W, kTM, P, 0)) return e;
   const int smem_bytes = a.bar_off + 512;
-  const int64_t grid = (int64_t)B * H * a.n_wtiles;
-  PMT_CHECK_ARG(grid < (1ll << 31), "corr1d tc: grid too large");
+  const int64_t tiles = (int64_t)B * H * a.n_wtiles;
+  PMT_CHECK_ARG(tiles < (1ll << 31), "corr1d tc: too many tiles");
+  a.n_tiles = (int)tiles;
+  const int64_t grid = tiles < sm_count() ? tiles : sm_count();  // persistent: one CTA per SM
   if (passes == 3) {
     PMT_CUDA_OK(cudaFuncSetAttribute(corr1d_fwd_tc_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
     corr1d_fwd_tc_kernel<3><<<(unsigned)grid, 320, smem_bytes, st>>>(tmL, tmR, tmO, a);

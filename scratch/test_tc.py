@@ -10,7 +10,7 @@ def run(B, C, H, W, P, passes, check=True, iters=0):
     L = torch.randn(B, C, H, W, device=dev, generator=g); R = torch.randn(B, C, H, W, device=dev, generator=g)
     ref = torch.empty(B, 1, P, H, W, device=dev); out = torch.full((B, 1, P, H, W), float('nan'), device=dev)
     st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
-    assert lib.pmt_corr1d_fwd_f32(vp(L), vp(R), vp(ref), B, C, H, W, P, 1, st) == 0
+    assert lib.pmt_corr1d_fwd_simt_f32(vp(L), vp(R), vp(ref), B, C, H, W, P, 1, st) == 0
     rc = lib.pmt_corr1d_fwd_tc_f32(vp(L), vp(R), vp(out), B, C, H, W, P, 1, passes, st)
     if rc != 0:
         print("rc", rc, lib.pmt_last_error()); return

@@ -11,7 +11,7 @@ def run(B, C, H, W, P, passes, iters=0):
     r1 = torch.empty_like(L); r2 = torch.empty_like(L)
     g1 = torch.full_like(L, float('nan')); g2 = torch.full_like(L, float('nan'))
     st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
-    assert lib.pmt_corr1d_bwd_f32(vp(L), vp(R), vp(G), vp(r1), vp(r2), B, C, H, W, P, 1, st) == 0
+    assert lib.pmt_corr1d_bwd_simt_f32(vp(L), vp(R), vp(G), vp(r1), vp(r2), B, C, H, W, P, 1, st) == 0
     rc = lib.pmt_corr1d_bwd_tc_f32(vp(L), vp(R), vp(G), vp(g1), vp(g2), B, C, H, W, P, 1, passes, st)
     if rc != 0:
         print("rc", rc, lib.pmt_last_error()); return
