@@ -1,0 +1,151 @@
+#!/usr/bin/env python
+"""bench_ops.py -- per-op device timings and roofline fractions for every row of SURVEY.md section 8(a):
+correlation engines (incl. BASELINE config 4, C=128 540x960), concat volume, soft-argmin / disparityregression,
+apply_disparity.  One JSON object per line.  Inputs resident in HBM, CUDA events, rotating buffers > L2.
+
+    python bench_ops.py [--iters 50] [--out profiles/ops.jsonl]
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes
+import json
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+
+def main():
+    import torch
+
+    import pmt_learning_for_semantic_segmentation_and_disparity_b200 as pmt
+
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--iters", type=int, default=50)
+    ap.add_argument("--out", default="")
+    args = ap.parse_args()
+    dev = torch.device("cuda:0")
+    lib = pmt.load_library()
+    hbm = 6525.2
+    mp = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(mp):
+        hbm = float(json.load(open(mp))["hbm_gbs"])
+    vp = lambda t: ctypes.c_void_p(t.data_ptr())
+    sp = ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+    lines = []
+
+    def timed(fn, n_sets):
+        for i in range(5):
+            fn(i % n_sets)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(args.iters):
+            fn(i % n_sets)
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / args.iters
+
+    def report(op, cfg, ms, alg_bytes, pairs, extra=None):
+        gbs = alg_bytes / (ms * 1e-3) * 1e-9
+        d = {"op": op, "config": cfg, "ms_per_launch": ms, "pairs_per_s": pairs / (ms * 1e-3),
+             "algorithmic_bytes": alg_bytes, "achieved_gbs": gbs, "hbm_peak_gbs": hbm, "hbm_frac": gbs / hbm}
+        if extra:
+            d.update(extra)
+        lines.append(d)
+        print(json.dumps(d), flush=True)
+
+    # ---- correlation engines ------------------------------------------------------------------------
+    for (B, C, H, W, P, tag) in [(4, 64, 256, 512, 192, "headline C=64 256x512 D=192"),
+                                 (1, 128, 540, 960, 192, "config4 C=128 540x960 D=192"),
+                                 (4, 352, 32, 64, 17, "production minidsnetExt call C=352 32x64 P=17"),
+                                 (2, 64, 64, 128, 40, "config1 C=64 64x128 P=40")]:
+        n_sets = 2
+        S = [dict(L=torch.randn(B, C, H, W, device=dev), R=torch.randn(B, C, H, W, device=dev),
+                  G=torch.randn(B, 1, P, H, W, device=dev), out=torch.empty(B, 1, P, H, W, device=dev),
+                  gL=torch.empty(B, C, H, W, device=dev), gR=torch.empty(B, C, H, W, device=dev)) for _ in range(n_sets)]
+        feat, vol = 4 * C * H * W, 4 * P * H * W
+        fb, bb = B * (2 * feat + vol), B * (vol + 4 * feat)
+        r = (P - 1) // 2
+        macs = C * H * sum(max(0, W - abs(q - r)) for q in range(P))
+        engines = {"auto": ("pmt_corr1d_fwd_f32", "pmt_corr1d_bwd_f32", ()),
+                   "simt": ("pmt_corr1d_fwd_simt_f32", "pmt_corr1d_bwd_simt_f32", ()),
+                   "tf32": ("pmt_corr1d_fwd_tc_f32", "pmt_corr1d_bwd_tc_f32", (1,))}
+        for name, (ff, bf, ex) in engines.items():
+            def fwd(i, ff=ff, ex=ex):
+                s = S[i]
+                return getattr(lib, ff)(vp(s["L"]), vp(s["R"]), vp(s["out"]), B, C, H, W, P, 1, *ex, sp)
+
+            def bwd(i, bf=bf, ex=ex):
+                s = S[i]
+                return getattr(lib, bf)(vp(s["L"]), vp(s["R"]), vp(s["G"]), vp(s["gL"]), vp(s["gR"]), B, C, H, W, P, 1, *ex, sp)
+
+            if fwd(0) != 0 or bwd(0) != 0:
+                continue  # engine does not support the shape (e.g. tensor-core backward needs C <= 128)
+            engine_id = lib.pmt_corr1d_uses_fast_path(vp(S[0]["L"]), vp(S[0]["R"]), vp(S[0]["G"]), C, H, W, P, 1)
+            ms_f, ms_b = timed(fwd, n_sets), timed(bwd, n_sets)
+            report(f"corr1d_fwd[{name}]", tag, ms_f, fb, B, {"useful_tflops": B * 2 * macs / (ms_f * 1e-3) * 1e-12,
+                                                               "default_engine_id": engine_id})
+            report(f"corr1d_bwd[{name}]", tag, ms_b, bb, B, {"useful_tflops": B * 4 * macs / (ms_b * 1e-3) * 1e-12})
+        del S
+        torch.cuda.empty_cache()
+
+    # ---- PSMNet ops (config 3: B=4, 32ch 64x128 -> (64,48,64,128); cost (4,192,256,512)) ---------------
+    B, C, D, H, W = 4, 32, 48, 64, 128
+    ref = [torch.randn(B, C, H, W, device=dev) for _ in range(2)]
+    tgt = [torch.randn(B, C, H, W, device=dev) for _ in range(2)]
+    cost = [torch.empty(B, 2 * C, D, H, W, device=dev) for _ in range(2)]
+    gref, gtgt = torch.empty(B, C, H, W, device=dev), torch.empty(B, C, H, W, device=dev)
+    vb, fbts = 4 * B * 2 * C * D * H * W, 4 * B * 2 * C * H * W
+    ms = timed(lambda i: lib.pmt_concat_volume_fwd_f32(vp(ref[i]), vp(tgt[i]), vp(cost[i]), B, C, D, H, W, 0, sp), 2)
+    report("concat_volume_fwd", "config3 B=4 (32,64,128)->(64,48,64,128)", ms, vb + fbts, B)
+    ms = timed(lambda i: lib.pmt_concat_volume_bwd_f32(vp(cost[i]), vp(gref), vp(gtgt), B, C, D, H, W, 0, sp), 2)
+    report("concat_volume_bwd", "config3", ms, vb + fbts, B)
+    del cost
+    B, D, H, W = 4, 192, 256, 512
+    c = [4 * torch.randn(B, D, H, W, device=dev) for _ in range(2)]
+    gc = torch.empty(B, D, H, W, device=dev)
+    out, lse, go = (torch.empty(B, H, W, device=dev) for _ in range(3))
+    go.normal_()
+    cb, ob = 4 * B * D * H * W, 4 * B * H * W
+    ms = timed(lambda i: lib.pmt_softargmin_fwd_f32(vp(c[i]), vp(out), vp(lse), B, D, H, W, sp), 2)
+    report("softargmin_fwd", "config3 cost (4,192,256,512)", ms, cb + 2 * ob, B)
+    ms = timed(lambda i: lib.pmt_softargmin_bwd_f32(vp(c[i]), vp(out), vp(lse), vp(go), vp(gc), B, D, H, W, sp), 2)
+    report("softargmin_bwd", "config3", ms, 2 * cb + 3 * ob, B)
+    ms = timed(lambda i: lib.pmt_dispreg_fwd_f32(vp(c[i]), vp(out), B, D, H, W, sp), 2)
+    report("dispreg_fwd", "config3", ms, cb + ob, B)
+    ms = timed(lambda i: lib.pmt_dispreg_bwd_f32(vp(go), vp(gc), B, D, H, W, sp), 2)
+    report("dispreg_bwd", "config3", ms, cb + ob, B)
+    # the reference's own op sequence on the same GPU (softmax -> repeat ramp -> mul -> sum), for context
+    ramp = torch.arange(D, device=dev, dtype=torch.float32).view(1, D, 1, 1)
+    ms = timed(lambda i: torch.sum(torch.softmax(c[i], dim=1) * ramp.repeat(B, 1, H, W), 1), 2)
+    report("softargmin_fwd[ATen sequence of the reference]", "config3", ms, cb + 2 * ob, B)
+    del c, gc
+
+    # ---- warp (config 4: 540x960, C=3; production 256x512 C=2) --------------------------------------
+    for (N, C, H, W) in [(4, 3, 540, 960), (4, 2, 256, 512), (1, 128, 540, 960)]:
+        img = torch.randn(N, C, H, W, device=dev)
+        off = -64.0 * torch.rand(N, 1, H, W, device=dev)
+        o = torch.empty(C, N, H, W, device=dev)
+        g = torch.randn(C, N, H, W, device=dev)
+        gi, gof = torch.zeros_like(img), torch.empty_like(off)
+        ms = timed(lambda i: lib.pmt_warp1d_fwd_f32(vp(img), vp(off), vp(o), N, C, H, W, 1, sp), 1)
+        report("warp1d_fwd", f"N={N} C={C} {H}x{W}", ms, 4 * N * H * W * (2 * C + 1), N)
+
+        def wb(i):
+            gi.zero_()
+            return lib.pmt_warp1d_bwd_f32(vp(img), vp(off), vp(g), vp(gi), vp(gof), N, C, H, W, 1, sp)
+
+        ms = timed(wb, 1)
+        report("warp1d_bwd (+zero fill of gimg)", f"N={N} C={C} {H}x{W}", ms, 4 * N * H * W * (3 * C + 2), N)
+
+    if args.out:
+        with open(args.out, "w") as f:
+            for d in lines:
+                f.write(json.dumps(d) + "\n")
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,63 @@
+#!/usr/bin/env python
+"""bench_step.py -- data-parallel training step (BASELINE configs 2 and 5): SDNetLite (DenseNet-121 siamese tower,
+1x17 correlation, decoders, disparity warp) fwd + loss + bwd + Adam on synthetic 256x512 stereo pairs, batch 4 per
+GPU, DDP + nn.SyncBatchNorm over NCCL/NVLink.  One process per GPU:
+
+    python bench_step.py --steps 30                                        # 1 GPU (config 2)
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29533 \
+        bench_step.py --steps 30                                           # config 5 (global batch 32)
+
+Device time of K steps between barriers, max over ranks; rank 0 prints one JSON line (pairs/s over all ranks).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+
+def main():
+    import torch
+
+    from pmt_learning_for_semantic_segmentation_and_disparity_b200 import harness, sharding
+
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--steps", type=int, default=30)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--batch", type=int, default=4)
+    ap.add_argument("--no-sync-bn", action="store_true")
+    args = ap.parse_args()
+    world = sharding.init_world("nccl" if int(os.environ.get("WORLD_SIZE", "1")) > 1 else None)
+    dev = torch.device("cuda", world.local_rank)
+    torch.cuda.set_device(dev)
+    step, model = harness.build_training_step(world, batch_per_gpu=args.batch, sync_bn=not args.no_sync_bn)
+    for _ in range(max(args.warmup, 3)):
+        loss = step()
+    torch.cuda.synchronize(dev)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    sharding.barrier(world)
+    torch.cuda.synchronize(dev)
+    e0.record()
+    for _ in range(args.steps):
+        loss = step()
+    e1.record()
+    torch.cuda.synchronize(dev)
+    sharding.barrier(world)
+    value, ms = sharding.throughput(world, args.batch * args.steps, e0.elapsed_time(e1))
+    if world.is_main:
+        n_params = sum(p.numel() for p in model.parameters())
+        print(json.dumps({"metric": "SDNetLite training step pairs/s (256x512, batch 4/GPU, DDP+SyncBN)", "value": value,
+                          "unit": "pairs/s", "n_gpus": world.world_size, "steps": args.steps,
+                          "ms_per_step": ms / args.steps, "scaling": "weak", "global_batch": args.batch * world.world_size,
+                          "params": n_params, "loss": float(loss), "sync_bn": not args.no_sync_bn,
+                          "collectives": "DDP gradient all-reduce + SyncBatchNorm statistics (NCCL); none in the hot-path ops"}),
+              flush=True)
+    sharding.shutdown(world)
+
+
+if __name__ == "__main__":
+    main()

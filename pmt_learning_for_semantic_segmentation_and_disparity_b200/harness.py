@@ -1,0 +1,105 @@
+"""Data-parallel training-step harness around the hot path (BASELINE configs 2 and 5).
+
+The reference's models (models/dsnet_t2.py::minidsnetExt etc.) cannot travel to the GPU box and are out of scope as
+build targets; what matters for row (e) is the SHAPE of the step they run: a siamese DenseNet-121 tower on
+left/right 256x512 images, the 1x17 correlation of the two 352-channel 1/8-resolution feature maps
+(models/dsnet_t2.py:1159-1160,1188), a 1x1 `corrConv2d` 17->128 + ReLU (:1197), decoders for disparity and
+segmentation, the disparity-guided warp of the right branch (models/dsnet_t2_warp.py:697-698), CE + L1 losses and
+Adam(lr=1.5e-3, eps=1e-7) (torch_implementation.py:279-305,724), under DistributedDataParallel with
+nn.SyncBatchNorm (torch_implementation.py:739-741).  `SDNetLite` reproduces that call pattern with this package's
+ops on the hot path; everything else is stock torch/cuDNN (out of scope).  The only collectives are DDP's gradient
+all-reduce and SyncBatchNorm's statistics exchange -- the hot-path ops never communicate.
+"""
+from __future__ import annotations
+
+import torch
+import torch.nn.functional as F
+from torch import nn
+
+from .correlation import SpatialCorrelationSampler
+from .warp import apply_disparity
+
+
+def _cbr(cin, cout, k=3, s=1):
+    return nn.Sequential(nn.Conv2d(cin, cout, k, s, k // 2, bias=False), nn.BatchNorm2d(cout), nn.ReLU(inplace=True))
+
+
+class SDNetLite(nn.Module):
+    """Joint segmentation + disparity net with the reference's hot-path call pattern (1dcorr, max_disp 8 at 1/8)."""
+
+    def __init__(self, n_labels: int = 2, feat_ch: int = 352, max_disp: int = 8, backbone: str = "densenet121"):
+        super().__init__()
+        if backbone == "densenet121":
+            import torchvision
+
+            f = torchvision.models.densenet121(weights=None).features
+            self.tower = nn.Sequential(f.conv0, f.norm0, f.relu0, f.pool0, f.denseblock1, f.transition1, f.denseblock2)
+            tower_ch = 512
+        else:  # small tower for CPU/unit tests
+            self.tower = nn.Sequential(_cbr(3, 32, 3, 2), _cbr(32, 64, 3, 2), _cbr(64, 96, 3, 2))
+            tower_ch = 96
+        self.reduce = _cbr(tower_ch, feat_ch, 1)
+        self.patch = 2 * max_disp + 1                                   # patch_corr = (1, max_disp*2+1)
+        self.correlation_sampler = SpatialCorrelationSampler(kernel_size=1, patch_size=(1, self.patch), stride=1,
+                                                             padding=0, dilation_patch=1)
+        self.corrConv2d = nn.Sequential(nn.Conv2d(self.patch, 128, 1), nn.ReLU(inplace=True))
+        self.skip = _cbr(feat_ch, 64, 1)
+        self.dec = nn.Sequential(_cbr(128 + 64, 128), _cbr(128, 64))
+        self.disp_head = nn.Conv2d(64, 1, 3, 1, 1)
+        self.seg_l = nn.Sequential(_cbr(feat_ch, 64), nn.Conv2d(64, n_labels, 3, 1, 1))
+        self.seg_r = nn.Sequential(_cbr(feat_ch, 64), nn.Conv2d(64, n_labels, 3, 1, 1))
+        self.att = nn.Sequential(nn.Conv2d(1, 1, 3, 1, 1), nn.Sigmoid())
+
+    def forward(self, left, right):
+        H, W = left.shape[-2:]
+        a = self.reduce(self.tower(left))
+        b = self.reduce(self.tower(right))
+        y = self.correlation_sampler(a, b)                              # (B,1,17,h,w)
+        y = torch.squeeze(y, dim=1)                                     # 1dcorr: not divided by C
+        y = self.corrConv2d(y)
+        x = self.dec(torch.cat([y, self.skip(a)], 1))
+        disp = F.interpolate(self.disp_head(x), size=(H, W), mode="bilinear", align_corners=False) * 8.0
+        seg_left = F.interpolate(self.seg_l(a), size=(H, W), mode="bilinear", align_corners=False)
+        seg_right = F.interpolate(self.seg_r(b), size=(H, W), mode="bilinear", align_corners=False)
+        warped = apply_disparity(seg_right, -disp)                      # sample the right branch at w - d
+        at_d = self.att(disp)
+        seg_both = (1 - at_d) * seg_left + at_d * warped
+        return seg_left, disp, seg_both, disp
+
+
+def sdnet_loss(outputs, seg_target, disp_target):
+    seg1, disp1, seg2, _ = outputs
+    return (F.cross_entropy(seg1, seg_target) + F.cross_entropy(seg2, seg_target)
+            + F.l1_loss(disp1.squeeze(1), disp_target))
+
+
+def synthetic_batch(batch: int, h: int, w: int, n_labels: int, device, generator=None):
+    left = torch.rand(batch, 3, h, w, device=device, generator=generator)
+    right = torch.rand(batch, 3, h, w, device=device, generator=generator)
+    disp = 64.0 * torch.rand(batch, h, w, device=device, generator=generator)
+    seg = torch.randint(0, n_labels, (batch, h, w), device=device, generator=generator)
+    return left, right, seg, disp
+
+
+def build_training_step(world, batch_per_gpu: int = 4, h: int = 256, w: int = 512, n_labels: int = 2,
+                        backbone: str = "densenet121", sync_bn: bool = True):
+    """Returns (step_fn, model): step_fn() runs one fwd + loss + bwd + Adam step on a fixed synthetic batch."""
+    dev = torch.device("cuda", world.local_rank)
+    torch.manual_seed(1234)  # identical initial weights on every rank
+    model = SDNetLite(n_labels=n_labels, backbone=backbone).to(dev)
+    if world.distributed:
+        if sync_bn:
+            model = nn.SyncBatchNorm.convert_sync_batchnorm(model)
+        model = nn.parallel.DistributedDataParallel(model, device_ids=[world.local_rank])
+    opt = torch.optim.Adam(model.parameters(), lr=1.5e-3, eps=1e-7)
+    g = torch.Generator(device=dev).manual_seed(world.rank)
+    left, right, seg, disp = synthetic_batch(batch_per_gpu, h, w, n_labels, dev, g)
+
+    def step():
+        opt.zero_grad(set_to_none=True)
+        loss = sdnet_loss(model(left, right), seg, disp)
+        loss.backward()
+        opt.step()
+        return loss
+
+    return step, model
