@@ -30,11 +30,17 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--batch", type=int, default=4)
     ap.add_argument("--no-sync-bn", action="store_true")
+    ap.add_argument("--eager", action="store_true", help="do not capture the step in a CUDA graph")
+    ap.add_argument("--graph", action="store_true",
+                    help="force CUDA-graph capture under DDP too (default: graph at 1 GPU, eager under DDP -- capturing "
+                         "DDP+SyncBatchNorm NCCL collectives hung on the 2-GPU box in round 1)")
     args = ap.parse_args()
     world = sharding.init_world("nccl" if int(os.environ.get("WORLD_SIZE", "1")) > 1 else None)
     dev = torch.device("cuda", world.local_rank)
     torch.cuda.set_device(dev)
-    step, model = harness.build_training_step(world, batch_per_gpu=args.batch, sync_bn=not args.no_sync_bn)
+    use_graph = args.graph or (not args.eager and world.world_size == 1)
+    step, model = harness.build_training_step(world, batch_per_gpu=args.batch, sync_bn=not args.no_sync_bn,
+                                               cuda_graph=use_graph)
     for _ in range(max(args.warmup, 3)):
         loss = step()
     torch.cuda.synchronize(dev)
@@ -53,7 +59,8 @@ def main():
         print(json.dumps({"metric": "SDNetLite training step pairs/s (256x512, batch 4/GPU, DDP+SyncBN)", "value": value,
                           "unit": "pairs/s", "n_gpus": world.world_size, "steps": args.steps,
                           "ms_per_step": ms / args.steps, "scaling": "weak", "global_batch": args.batch * world.world_size,
-                          "params": n_params, "loss": float(loss), "sync_bn": not args.no_sync_bn,
+                          "params": n_params, "loss": float(loss.detach()), "sync_bn": not args.no_sync_bn,
+                          "cuda_graph": use_graph,
                           "collectives": "DDP gradient all-reduce + SyncBatchNorm statistics (NCCL); none in the hot-path ops"}),
               flush=True)
     sharding.shutdown(world)

@@ -26,6 +26,8 @@ constexpr int kCK = 16;               // channels per ring stage (2 k-steps of 8
 constexpr int kBoxBytes = kCK * 128;  // one 32-column x 16-channel box
 constexpr int kLBlocks = kTM / 32;    // 4 boxes for the L tile
 constexpr int kMaxNB = 10;            // band boxes (P <= 193)
+constexpr int kRowsPerStep = 48;      // output planes per staging buffer / TMA store
+constexpr int kStepBytes = kRowsPerStep * kTM * 4;
 
 struct TcFwdArgs {
   int C, H, W, P, rW, delta;
@@ -33,10 +35,12 @@ struct TcFwdArgs {
   int N1, N2;            // MMA N of the two band halves (N2 may be 0)
   int tmem_cols;         // power of two >= 32*NB
   int n_wtiles, n_cchunks, n_tiles;
-  int stages;
-  int stage_bytes;       // (4+NB)*kBoxBytes * (hi+lo ? 2 : 1)
-  int lo_off;            // byte offset of the lo copy inside a stage
-  int tile_off;          // byte offset of the [P][128] staging tile
+  int stages;            // raw ring stages (TMA destination; the raw fp32 doubles as the tf32 "hi" operand)
+  int lo_stages;         // lo ring stages (3xTF32 only)
+  int stage_bytes;       // (4+NB)*kBoxBytes
+  int lo_ring_off;       // byte offset of the lo ring
+  int tile_off;          // byte offset of the two [48][128] staging buffers
+  int n_steps;           // epilogue steps of kRowsPerStep output planes
   int bar_off;           // byte offset of the barriers
   int debug;             // PMT_TC_DEBUG: 1 = constant tile, 2 = tcgen05.st pattern instead of MMA result
 };
@@ -55,7 +59,8 @@ corr1d_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmL, const __grid_const
   uint64_t* full = reinterpret_cast<uint64_t*>(smem + a.bar_off);
   uint64_t* empty = full + 8;
   uint64_t* xf_done = empty + 8;
-  uint64_t* tmem_full = xf_done + 8;
+  uint64_t* lo_empty = xf_done + 8;
+  uint64_t* tmem_full = lo_empty + 8;
   uint64_t* tmem_empty = tmem_full + 1;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 1);
 
@@ -66,7 +71,10 @@ corr1d_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmL, const __grid_const
     for (int s = 0; s < a.stages; ++s) {
       mbar_init(&full[s], 1);
       mbar_init(&empty[s], 1);
+    }
+    for (int s = 0; s < 8; ++s) {
       mbar_init(&xf_done[s], 4);
+      mbar_init(&lo_empty[s], 1);
     }
     mbar_init(tmem_full, 1);
     mbar_init(tmem_empty, 4);
@@ -123,9 +131,12 @@ corr1d_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmL, const __grid_const
         for (int k = 0; k < a.n_cchunks; ++k, ++g) {
           const int st = g % a.stages;
           const uint32_t ph = (uint32_t)(g / a.stages) & 1u;
-          mbar_wait(kPasses == 3 ? &xf_done[st] : &full[st], ph);
+          const int ls = g % a.lo_stages;
+          if (kPasses == 3) mbar_wait(&xf_done[ls], (uint32_t)(g / a.lo_stages) & 1u);
+          else mbar_wait(&full[st], ph);
           tc::fence_after_sync();
           const uint32_t sbase = smem_u32(smem + (size_t)st * a.stage_bytes);
+          const uint32_t lo_delta = smem_u32(smem + a.lo_ring_off + (size_t)ls * a.stage_bytes) - sbase;
 #pragma unroll
           for (int kk = 0; kk < kCK / 8 && !(a.debug & 16); ++kk) {
             const uint32_t acc = (k > 0 || kk > 0) ? 1u : 0u;
@@ -136,9 +147,9 @@ corr1d_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmL, const __grid_const
             const uint64_t dB1 = mn_desc(b1_hi, kBoxBytes, 1024);
             const uint64_t dB2 = mn_desc(b2_hi, kBoxBytes, 1024);
             if (kPasses == 3) {
-              const uint64_t dAl = mn_desc(a_hi + a.lo_off, kBoxBytes, 1024);
-              const uint64_t dB1l = mn_desc(b1_hi + a.lo_off, kBoxBytes, 1024);
-              const uint64_t dB2l = mn_desc(b2_hi + a.lo_off, kBoxBytes, 1024);
+              const uint64_t dAl = mn_desc(a_hi + lo_delta, kBoxBytes, 1024);
+              const uint64_t dB1l = mn_desc(b1_hi + lo_delta, kBoxBytes, 1024);
+              const uint64_t dB2l = mn_desc(b2_hi + lo_delta, kBoxBytes, 1024);
               // small cross terms first, then the dominant hi*hi term
               tc::mma_tf32(tmem_base, dAl, dB1, idesc1, acc);
               tc::mma_tf32(tmem_base, dA, dB1l, idesc1, 1u);
@@ -154,6 +165,7 @@ corr1d_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmL, const __grid_const
             }
           }
           tc::mma_commit(&empty[st]);  // ring slot reusable once these MMAs have read it
+          if (kPasses == 3) tc::mma_commit(&lo_empty[ls]);
         }
         tc::mma_commit(tmem_full);     // accumulator of this tile complete
       }
@@ -162,35 +174,41 @@ corr1d_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmL, const __grid_const
     // ===== epilogue warps: TMEM -> registers -> un-skewed staging tile -> TMA store =====
     const int q = wid & 3;               // TMEM lane quarter this warp may access
     const int wl = 32 * q + lane;        // output column within the tile (= TMEM lane)
-    float* tile_s = reinterpret_cast<float*>(smem + a.tile_off);
-    const int c_lo = (32 * q + a.delta) / 32;
-    int c_hi = (32 * q + 31 + a.delta + a.P - 1) / 32;
-    if (c_hi > a.NB - 1) c_hi = a.NB - 1;
-    int it = 0;
+    int it = 0, gstep = 0;
     for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x, ++it) {
       const int wt = tile % a.n_wtiles, h = (tile / a.n_wtiles) % a.H, n = tile / (a.n_wtiles * a.H);
       mbar_wait(tmem_full, (uint32_t)it & 1u);
       tc::fence_after_sync();
-      if (wid == 2 && lane == 0) tc::tma_store_wait_read<0>();  // previous tile's store has read the staging tile
-      named_bar_sync(1, 128);
-      for (int cb = c_lo; cb <= c_hi && !(a.debug & 8); ++cb) {
-        float v[32];
-        tc::tmem_ld32(tmem_base + ((uint32_t)(32 * q) << 16) + (uint32_t)(32 * cb), v);
-        const int pbase = 32 * cb - a.delta - wl;  // p of column jj is pbase + jj
+      // kRowsPerStep output planes at a time through two ping-pong staging buffers, one TMA store per step
+      for (int s = 0; s < a.n_steps; ++s, ++gstep) {
+        float* tile_s = reinterpret_cast<float*>(smem + a.tile_off + (gstep & 1) * kStepBytes);
+        const int p0 = kRowsPerStep * s;
+        if (wid == 2 && lane == 0) tc::tma_store_wait_read<1>();  // the store that last used this buffer has read it
+        named_bar_sync(1, 128);
+        const int c_lo = (p0 + a.delta + 32 * q) / 32;
+        int c_hi = (p0 + kRowsPerStep - 1 + a.delta + 32 * q + 31) / 32;
+        if (c_hi > a.NB - 1) c_hi = a.NB - 1;
+        for (int cb = c_lo; cb <= c_hi && !(a.debug & 8); ++cb) {
+          float v[32];
+          tc::tmem_ld32(tmem_base + ((uint32_t)(32 * q) << 16) + (uint32_t)(32 * cb), v);
+          const int pbase = 32 * cb - a.delta - wl - p0;  // plane (relative to p0) of column jj is pbase + jj
 #pragma unroll
-        for (int jj = 0; jj < 32; ++jj) {
-          const int p = pbase + jj;
-          if (p >= 0 && p < a.P) tile_s[p * kTM + wl] = v[jj];
+          for (int jj = 0; jj < 32; ++jj) {
+            const int pr = pbase + jj;
+            if (pr >= 0 && pr < kRowsPerStep && p0 + pr < a.P) tile_s[pr * kTM + wl] = v[jj];
+          }
         }
-      }
-      tc::fence_before_sync();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(tmem_empty);  // this warp's TMEM reads are done: the next tile's MMAs may start
-      fence_proxy_async();                     // generic-proxy writes -> visible to the TMA store
-      named_bar_sync(1, 128);
-      if (wid == 2 && lane == 0) {
-        tc::tma_store_4d(&tmO, tile_s, wt * kTM, h, 0, n);
-        tc::tma_store_commit();
+        if (s == a.n_steps - 1) {
+          tc::fence_before_sync();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(tmem_empty);  // TMEM drained: the next tile's MMAs may start
+        }
+        fence_proxy_async();                       // generic-proxy writes -> visible to the TMA store
+        named_bar_sync(1, 128);
+        if (wid == 2 && lane == 0) {
+          tc::tma_store_4d(&tmO, tile_s, wt * kTM, h, p0, n);
+          tc::tma_store_commit();
+        }
       }
     }
     if (wid == 2 && lane == 0) tc::tma_store_wait<0>();
@@ -203,24 +221,26 @@ corr1d_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmL, const __grid_const
       for (int k = 0; k < a.n_cchunks; ++k, ++g) {
         const int st = g % a.stages;
         const uint32_t ph = (uint32_t)(g / a.stages) & 1u;
+        const int ls = g % a.lo_stages;
         mbar_wait(&full[st], ph);
-        unsigned char* sbase = smem + (size_t)st * a.stage_bytes;
+        mbar_wait(&lo_empty[ls], ((uint32_t)(g / a.lo_stages) & 1u) ^ 1u);
+        const unsigned char* sbase = smem + (size_t)st * a.stage_bytes;
+        unsigned char* lbase = smem + a.lo_ring_off + (size_t)ls * a.stage_bytes;
+        // hi operand = the raw fp32 left in place (kind::tf32 ignores the low 13 mantissa bits, verified on B200:
+        // the 3-term sum stays at ~1e-6); lo = x - trunc_tf32(x) is exact in fp32 and goes to the lo ring.
 #pragma unroll 2
         for (int c = t; c < nchunks && !(a.debug & 4); c += 128) {
-          float4* p = reinterpret_cast<float4*>(sbase + 16 * c);
-          const float4 x = *p;
-          float4 hi, lo;
-          uint32_t u;
-          asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x.x)); hi.x = __uint_as_float(u); lo.x = x.x - hi.x;
-          asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x.y)); hi.y = __uint_as_float(u); lo.y = x.y - hi.y;
-          asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x.z)); hi.z = __uint_as_float(u); lo.z = x.z - hi.z;
-          asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x.w)); hi.w = __uint_as_float(u); lo.w = x.w - hi.w;
-          *p = hi;
-          *reinterpret_cast<float4*>(sbase + a.lo_off + 16 * c) = lo;
+          const float4 x = *reinterpret_cast<const float4*>(sbase + 16 * c);
+          float4 lo;
+          lo.x = x.x - __uint_as_float(__float_as_uint(x.x) & 0xffffe000u);
+          lo.y = x.y - __uint_as_float(__float_as_uint(x.y) & 0xffffe000u);
+          lo.z = x.z - __uint_as_float(__float_as_uint(x.z) & 0xffffe000u);
+          lo.w = x.w - __uint_as_float(__float_as_uint(x.w) & 0xffffe000u);
+          *reinterpret_cast<float4*>(lbase + 16 * c) = lo;
         }
         fence_proxy_async();  // make the rewritten stage visible to the tensor core's async-proxy reads
         __syncwarp();
-        if (lane == 0) mbar_arrive(&xf_done[st]);
+        if (lane == 0) mbar_arrive(&xf_done[ls]);
       }
     }
   }
@@ -247,17 +267,22 @@ int fill_args(TcFwdArgs* a, int C, int H, int W, int P, int passes) {
   a->n_wtiles = ceil_div(W, kTM);
   a->n_cchunks = ceil_div(C, kCK);
   a->n_tiles = 0;  // set by the launcher (needs B)
-  const int hi_bytes = (kLBlocks + a->NB) * kBoxBytes;
-  a->lo_off = hi_bytes;
-  a->stage_bytes = hi_bytes * (passes == 3 ? 2 : 1);
-  const int tile_bytes = round_up(P * kTM * 4, 1024);
-  const int budget = 227 * 1024 - 512 - tile_bytes;
-  int stages = budget / a->stage_bytes;
-  if (stages > 8) stages = 8;
-  if (stages < 1) return 1;
-  a->stages = stages;
-  a->tile_off = stages * a->stage_bytes;
-  a->bar_off = a->tile_off + tile_bytes;
+  a->stage_bytes = (kLBlocks + a->NB) * kBoxBytes;
+  a->n_steps = ceil_div(P, kRowsPerStep);
+  const int budget = 227 * 1024 - 1024 - 2 * kStepBytes;
+  int total = budget / a->stage_bytes;  // ring stages that fit next to the two staging buffers
+  if (passes == 3) {
+    a->lo_stages = total >= 6 ? 2 : 1;
+    a->stages = total - a->lo_stages;
+  } else {
+    a->lo_stages = 1;
+    a->stages = total;
+  }
+  if (a->stages > 8) a->stages = 8;
+  if (a->stages < 1) return 1;
+  a->lo_ring_off = a->stages * a->stage_bytes;
+  a->tile_off = a->lo_ring_off + (passes == 3 ? a->lo_stages * a->stage_bytes : 0);
+  a->bar_off = a->tile_off + 2 * kStepBytes;
   const char* dbg = getenv("PMT_TC_DEBUG");
   a->debug = dbg ? atoi(dbg) : 0;
   return 0;
@@ -271,7 +296,6 @@ int make_tmap_nchw_ex(CUtensorMap* map, const float* base, int B, int C, int H, 
 bool corr1d_fwd_tc_ok(const void* in1, const void* in2, const void* out, int C, int H, int W, int P, int dilp,
                       int passes) {
   if (dilp != 1 || P < 1 || C < 1 || W % 4 != 0 || !aligned16(in1) || !aligned16(in2) || !aligned16(out)) return false;
-  if (P > 256) return false;  // TMA store box limit
   TcFwdArgs a;
   (void)H;
   return fill_args(&a, C, H, W, P, passes) == 0;
@@ -285,7 +309,7 @@ int launch_corr1d_fwd_tc(const float* in1, const float* in2, float* out, int B, 
   CUtensorMap tmL, tmR, tmO;
   if (int e = make_tmap_nchw_ex(&tmL, in1, B, C, H, W, 32, kCK, 2)) return e;
   if (int e = make_tmap_nchw_ex(&tmR, in2, B, C, H, W, 32, kCK, 2)) return e;
-  if (int e = make_tmap_nchw_ex(&tmO, out, B, P, H, W, kTM, P, 0)) return e;
+  if (int e = make_tmap_nchw_ex(&tmO, out, B, P, H, W, kTM, kRowsPerStep, 0)) return e;
   const int smem_bytes = a.bar_off + 512;
   const int64_t tiles = (int64_t)B * H * a.n_wtiles;
   PMT_CHECK_ARG(tiles < (1ll << 31), "corr1d tc: too many tiles");

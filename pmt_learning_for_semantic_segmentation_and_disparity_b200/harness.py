@@ -82,24 +82,51 @@ def synthetic_batch(batch: int, h: int, w: int, n_labels: int, device, generator
 
 
 def build_training_step(world, batch_per_gpu: int = 4, h: int = 256, w: int = 512, n_labels: int = 2,
-                        backbone: str = "densenet121", sync_bn: bool = True):
-    """Returns (step_fn, model): step_fn() runs one fwd + loss + bwd + Adam step on a fixed synthetic batch."""
+                        backbone: str = "densenet121", sync_bn: bool = True, cuda_graph: bool = False):
+    """Returns (step_fn, model): step_fn() runs one fwd + loss + bwd + Adam step on a fixed synthetic batch.
+
+    cuda_graph=True captures the whole step -- forward, our hot-path kernels, backward, DDP's bucketed gradient
+    all-reduce, SyncBatchNorm's statistics collectives and the Adam update -- into ONE CUDA graph.  The eager step
+    is launch-bound (hundreds of tiny BN/NCCL launches per step, section 5.8 of SURVEY.md); replaying a graph
+    removes the host from the loop, which is what lets the step scale across GPUs."""
     dev = torch.device("cuda", world.local_rank)
     torch.manual_seed(1234)  # identical initial weights on every rank
     model = SDNetLite(n_labels=n_labels, backbone=backbone).to(dev)
-    if world.distributed:
-        if sync_bn:
-            model = nn.SyncBatchNorm.convert_sync_batchnorm(model)
-        model = nn.parallel.DistributedDataParallel(model, device_ids=[world.local_rank])
-    opt = torch.optim.Adam(model.parameters(), lr=1.5e-3, eps=1e-7)
-    g = torch.Generator(device=dev).manual_seed(world.rank)
-    left, right, seg, disp = synthetic_batch(batch_per_gpu, h, w, n_labels, dev, g)
+    side = torch.cuda.Stream(device=dev)
+    side.wait_stream(torch.cuda.current_stream(dev))
+    with torch.cuda.stream(side):  # DDP must be built and warmed up on the stream family the graph is captured from
+        if world.distributed:
+            if sync_bn:
+                model = nn.SyncBatchNorm.convert_sync_batchnorm(model)
+            model = nn.parallel.DistributedDataParallel(model, device_ids=[world.local_rank])
+        opt = torch.optim.Adam(model.parameters(), lr=1.5e-3, eps=1e-7, capturable=cuda_graph)
+        g = torch.Generator(device=dev).manual_seed(world.rank)
+        left, right, seg, disp = synthetic_batch(batch_per_gpu, h, w, n_labels, dev, g)
 
-    def step():
-        opt.zero_grad(set_to_none=True)
-        loss = sdnet_loss(model(left, right), seg, disp)
-        loss.backward()
+        def eager_step():
+            opt.zero_grad(set_to_none=True)
+            loss = sdnet_loss(model(left, right), seg, disp)
+            loss.backward()
+            opt.step()
+            return loss
+
+        if cuda_graph:
+            for _ in range(11):  # DDP needs >= 11 eager iterations before its collectives can be captured
+                eager_step()
+    torch.cuda.current_stream(dev).wait_stream(side)
+    if not cuda_graph:
+        return eager_step, model
+
+    graph = torch.cuda.CUDAGraph()
+    opt.zero_grad(set_to_none=True)
+    with torch.cuda.graph(graph):
+        static_loss = sdnet_loss(model(left, right), seg, disp)
+        static_loss.backward()
         opt.step()
-        return loss
 
-    return step, model
+    def graph_step():
+        graph.replay()
+        return static_loss
+
+    graph_step.graph = graph
+    return graph_step, model
