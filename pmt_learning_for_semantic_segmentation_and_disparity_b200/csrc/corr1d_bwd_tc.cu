@@ -52,6 +52,7 @@ struct TcBwdArgs {
   int band_slot_bytes, band_lo_off;   // band ring slot: hi [Cbox*128] (+ lo)
   int gd_off, band_off, bar_off;      // byte offsets in dynamic shared memory (raw ring at 0)
   int tmem_cols;
+  int acc_cols;        // TMEM columns per accumulator (Cbox, or 2*Cbox for 3xTF32: hi and lo column blocks)
   TcBwdMode m[2];
   int debug;           // PMT_TC_DEBUG ablation bits: 4 skip Gd build, 32 skip band split, 16 skip MMA, 8 skip epilogue
 };
@@ -61,11 +62,10 @@ __device__ __forceinline__ uint32_t kmajor_off(int row, int col) {
   return (uint32_t)((row >> 3) * 1024 + (row & 7) * 128 + ((((col >> 2) ^ (row & 7)) << 4) | ((col & 3) << 2)));
 }
 
-__device__ __forceinline__ void split_tf32(float x, float& hi, float& lo) {
-  uint32_t u;
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x));
-  hi = __uint_as_float(u);
-  lo = x - hi;
+// 3xTF32 split.  kind::tf32 reads only the top 19 bits of an fp32 operand (verified on B200), so the raw value
+// can serve as the "hi" operand and lo = x - trunc_tf32(x) (exact in fp32) carries the remaining 13 bits.
+__device__ __forceinline__ float lo_tf32(float x) {
+  return x - __uint_as_float(__float_as_uint(x) & 0xffffe000u);
 }
 
 struct TileCoord {
@@ -183,12 +183,13 @@ corr1d_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmIn1, const __grid_con
     // ===== MMA issuer =====
     if (lane == 0) {
       const uint32_t idesc = tc::make_idesc(2, 0, 0, kTM, a.Cbox);
+      const uint32_t idesc2 = tc::make_idesc(2, 0, 0, kTM, 2 * a.Cbox);  // B = [band_hi ; band_lo] stacked along N
       int g = 0;
       for (int i = 0; i < n_my; ++i) {
         const int buf = i & 1;
         mbar_wait(&tmem_empty[buf], ((uint32_t)(i >> 1) & 1u) ^ 1u);  // epilogue drained this accumulator
         tc::fence_after_sync();
-        const uint32_t d_tmem = tmem_base + (uint32_t)(buf * a.Cbox);
+        const uint32_t d_tmem = tmem_base + (uint32_t)(buf * a.acc_cols);
         for (int k = 0; k < a.NKC; ++k, ++g) {
           const int gs = g % a.gd_slots, bs = g % a.band_slots;
           mbar_wait(&gd_built[gs], (uint32_t)(g / a.gd_slots) & 1u);
@@ -203,11 +204,11 @@ corr1d_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmIn1, const __grid_con
             const uint64_t dA = tc::smem_desc(sa + kk * 32, 16, 1024, 2);
             const uint64_t dB = tc::smem_desc(sb + kk * 32, 16, 1024, 2);
             if (kPasses == 3) {
+              // D[:, 0:C] += A_hi*B_hi + A_lo*B_hi ; D[:, C:2C] += A_hi*B_lo  (A_hi is read once for both B halves;
+              // the epilogue adds the two column blocks)
               const uint64_t dAl = tc::smem_desc(sa + a.gd_lo_off + kk * 32, 16, 1024, 2);
-              const uint64_t dBl = tc::smem_desc(sb + a.band_lo_off + kk * 32, 16, 1024, 2);
-              tc::mma_tf32(d_tmem, dAl, dB, idesc, acc);
-              tc::mma_tf32(d_tmem, dA, dBl, idesc, 1u);
-              tc::mma_tf32(d_tmem, dA, dB, idesc, 1u);
+              tc::mma_tf32(d_tmem, dA, dB, idesc2, acc);
+              tc::mma_tf32(d_tmem, dAl, dB, idesc, 1u);
             } else {
               tc::mma_tf32(d_tmem, dA, dB, idesc, acc);
             }
@@ -232,7 +233,13 @@ corr1d_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmIn1, const __grid_con
       float* o = dst + ((int64_t)tc_.n * a.C * a.H + tc_.h) * (int64_t)a.W + tc_.x0 + xl;
       for (int cb = 0; cb < a.Cbox && !(a.debug & 8); cb += 32) {
         float v[32];
-        tc::tmem_ld32(tmem_base + ((uint32_t)(32 * q) << 16) + (uint32_t)(buf * a.Cbox + cb), v);
+        tc::tmem_ld32(tmem_base + ((uint32_t)(32 * q) << 16) + (uint32_t)(buf * a.acc_cols + cb), v);
+        if (kPasses == 3) {
+          float v2[32];
+          tc::tmem_ld32(tmem_base + ((uint32_t)(32 * q) << 16) + (uint32_t)(buf * a.acc_cols + a.Cbox + cb), v2);
+#pragma unroll
+          for (int cc = 0; cc < 32; ++cc) v[cc] += v2[cc];
+        }
 #pragma unroll
         for (int cc = 0; cc < 32; ++cc)
           if (ok && cb + cc < a.C) o[(int64_t)(cb + cc) * pstride] = v[cc];
@@ -270,17 +277,10 @@ corr1d_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmIn1, const __grid_con
               v[t] = (p >= 0 && p < a.P) ? Gt[p * kTM + xl] : 0.f;
             }
             const uint32_t off = kmajor_off(xl, 4 * c4);
-            if (kPasses == 3) {
-              float4 hi, lo;
-              split_tf32(v[0], hi.x, lo.x);
-              split_tf32(v[1], hi.y, lo.y);
-              split_tf32(v[2], hi.z, lo.z);
-              split_tf32(v[3], hi.w, lo.w);
-              *reinterpret_cast<float4*>(sa + off) = hi;
-              *reinterpret_cast<float4*>(sa + a.gd_lo_off + off) = lo;
-            } else {
-              *reinterpret_cast<float4*>(sa + off) = make_float4(v[0], v[1], v[2], v[3]);
-            }
+            *reinterpret_cast<float4*>(sa + off) = make_float4(v[0], v[1], v[2], v[3]);
+            if (kPasses == 3)
+              *reinterpret_cast<float4*>(sa + a.gd_lo_off + off) =
+                  make_float4(lo_tf32(v[0]), lo_tf32(v[1]), lo_tf32(v[2]), lo_tf32(v[3]));
           }
           // recycle the boxes whose last reader was this chunk (the next tile's loads may land in them)
           __syncwarp();
@@ -308,14 +308,8 @@ corr1d_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmIn1, const __grid_con
               const int xl = 4 * r + t;
               const float v = raw[(xl + 31 - lane) * kKC + lane];   // g[p_first + xl + 31 - jj][column jj]
               const uint32_t off = kmajor_off(xl, lane);
-              if (kPasses == 3) {
-                float hi, lo;
-                split_tf32(v, hi, lo);
-                *reinterpret_cast<float*>(sa + off) = hi;
-                *reinterpret_cast<float*>(sa + a.gd_lo_off + off) = lo;
-              } else {
-                *reinterpret_cast<float*>(sa + off) = v;
-              }
+              *reinterpret_cast<float*>(sa + off) = v;
+              if (kPasses == 3) *reinterpret_cast<float*>(sa + a.gd_lo_off + off) = lo_tf32(v);
             }
           }
           __syncwarp();
@@ -328,15 +322,9 @@ corr1d_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmIn1, const __grid_con
           unsigned char* sb = band_ring + (size_t)bs * a.band_slot_bytes;
           const int nch = band_bytes / 16;
           for (int c = (bw * 32 + lane); c < nch && !(a.debug & 32); c += kBuilders * 32) {
-            float4* q = reinterpret_cast<float4*>(sb + 16 * c);
-            const float4 x = *q;
-            float4 hi, lo;
-            split_tf32(x.x, hi.x, lo.x);
-            split_tf32(x.y, hi.y, lo.y);
-            split_tf32(x.z, hi.z, lo.z);
-            split_tf32(x.w, hi.w, lo.w);
-            *q = hi;
-            *reinterpret_cast<float4*>(sb + a.band_lo_off + 16 * c) = lo;
+            const float4 x = *reinterpret_cast<const float4*>(sb + 16 * c);
+            *reinterpret_cast<float4*>(sb + a.band_lo_off + 16 * c) =
+                make_float4(lo_tf32(x.x), lo_tf32(x.y), lo_tf32(x.z), lo_tf32(x.w));
           }
         }
         fence_proxy_async();
@@ -387,8 +375,10 @@ int fill_args(TcBwdArgs* a, int C, int H, int W, int P, int passes) {
   a->gd_off = raw_bytes;
   a->band_off = a->gd_off + a->gd_slots * a->gd_slot_bytes;
   a->bar_off = a->band_off + a->band_slots * a->band_slot_bytes;
+  a->acc_cols = a->Cbox * (passes == 3 ? 2 : 1);
+  if (2 * a->acc_cols > 512) return 1;
   int cols = 32;
-  while (cols < 2 * a->Cbox) cols *= 2;
+  while (cols < 2 * a->acc_cols) cols *= 2;
   a->tmem_cols = cols;
   const char* dbg = getenv("PMT_TC_DEBUG");
   a->debug = dbg ? atoi(dbg) : 0;
