@@ -6,7 +6,7 @@
 //   D[x (M=128 TMEM lanes)][c (N=C columns)] = sum over the band (K = 32*NKC columns, 320 for P=192).
 // Persistent CTAs (one per SM, half of them per gradient) walk tiles with every stage of the pipeline
 // running ahead across tile boundaries:
-//   * warp 0 (TMA producer): the feature band = B operand (rows c, K contiguous along w -> K-major), one
+//   * warps 0 and 14 (TMA producers): the feature band = B operand (rows c, K contiguous along w -> K-major), one
 //     128-byte-swizzled [C][32] box per K chunk into a deep ring; raw g into a second ring -- mode 0: the
 //     tile's [P][128] slice as 32-row boxes (a box is recycled for the next tile as soon as its last
 //     chunk is built), mode 1: one [160][32] block per chunk (OOB rows/columns zero-filled by TMA);
@@ -28,7 +28,7 @@ constexpr int kKC = 32;                   // band columns per K chunk (4 k-steps
 constexpr int kGdBytes = kTM * kKC * 4;   // 16 KB: one A-operand chunk
 constexpr int kEpiWarps = 4;
 constexpr int kBuilders = 8;
-constexpr int kThreads = 32 * (2 + kEpiWarps + kBuilders);  // 448
+constexpr int kThreads = 32 * (3 + kEpiWarps + kBuilders);  // 480: band producer, MMA, 4 epilogue, 8 builders, raw-g producer
 constexpr int kBox0Bytes = 32 * kTM * 4;          // mode 0: 32 rows of g x 128 columns (16 KB)
 constexpr int kRawRows1 = 160;                    // mode 1: rows of a raw block (>= 128+32-1)
 constexpr int kRawSlot1 = kRawRows1 * kKC * 4;    // 20 KB
@@ -137,45 +137,39 @@ corr1d_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmIn1, const __grid_con
   const uint32_t tmem_base = *tmem_slot;
 
   if (wid == 0) {
-    // ===== TMA producer: raw g runs kPre chunks ahead of the band, both rings span tile boundaries =====
+    // ===== TMA producer 1: the feature band, one swizzled [C][32] box per K chunk, ring spans tile boundaries =====
     if (lane == 0) {
       tma_prefetch_desc(tmBand);
-      // Prefetch distance of the raw-g ring.  Mode 0: the slot of box k is released by the previous tile's
-      // chunk min(NKC-1, k+koff); that chunk must already have its band issued or the producer would wait on
-      // work it has not fed yet.  Mode 1: 4 slots, a slot is released by the chunk 4 positions earlier.
-      int kPre = 2;
-      if (mode == 0) {
-        const int ke = m.koff < a.NKC - 1 ? m.koff : a.NKC - 1;
-        kPre = a.NKC - ke - 1;
-        kPre = kPre < 0 ? 0 : (kPre > 3 ? 3 : kPre);
+      for (int g = 0; g < G; ++g) {
+        const int i = g / a.NKC, k = g - i * a.NKC;
+        const TileCoord tc_ = tile_coord(a, i);
+        const int bs = g % a.band_slots;
+        mbar_wait(&band_empty[bs], ((uint32_t)(g / a.band_slots) & 1u) ^ 1u);
+        mbar_arrive_expect_tx(&band_full[bs], (uint32_t)band_bytes);
+        tma_load_4d(band_ring + (size_t)bs * a.band_slot_bytes, tmBand, tc_.x0 + m.oo + kKC * k, tc_.h, 0, tc_.n,
+                    &band_full[bs]);
       }
-      for (int g = -kPre; g < G; ++g) {
-        const int gp = g + kPre;
-        if (gp < G) {
-          const int i = gp / a.NKC, k = gp - i * a.NKC;
-          const TileCoord tc_ = tile_coord(a, i);
-          if (mode == 0) {
-            if (k < a.n_gboxes) {
-              mbar_wait(&raw_empty[k], ((uint32_t)i & 1u) ^ 1u);  // previous tile is done with this box
-              mbar_arrive_expect_tx(&raw_full[k], (uint32_t)kBox0Bytes);
-              tma_load_4d(smem + k * kBox0Bytes, &tmG0, tc_.x0, tc_.h, 32 * k, tc_.n, &raw_full[k]);
-            }
-          } else {
-            const int slot = gp % kRawSlots1;
-            mbar_wait(&raw_empty[slot], ((uint32_t)(gp / kRawSlots1) & 1u) ^ 1u);
-            mbar_arrive_expect_tx(&raw_full[slot], (uint32_t)kRawSlot1);
-            tma_load_4d(smem + slot * kRawSlot1, &tmG1, tc_.x0 + m.oo + kKC * k, tc_.h,
-                        a.P - 1 + m.delta - kKC * k - (kKC - 1), tc_.n, &raw_full[slot]);
+    }
+  } else if (wid == 2 + kEpiWarps + kBuilders) {
+    // ===== TMA producer 2: raw g.  Mode 0: 32-row boxes of the tile's [P][128] slice, box k lives in slot k and is
+    // reloaded for the next tile as soon as the builders release it; mode 1: one [160][32] block per chunk.  It
+    // only waits on slot releases from the builders, so it runs as far ahead as the ring allows. =====
+    if (lane == 0) {
+      for (int g = 0; g < G; ++g) {
+        const int i = g / a.NKC, k = g - i * a.NKC;
+        const TileCoord tc_ = tile_coord(a, i);
+        if (mode == 0) {
+          if (k < a.n_gboxes) {
+            mbar_wait(&raw_empty[k], ((uint32_t)i & 1u) ^ 1u);  // previous tile is done with this box
+            mbar_arrive_expect_tx(&raw_full[k], (uint32_t)kBox0Bytes);
+            tma_load_4d(smem + k * kBox0Bytes, &tmG0, tc_.x0, tc_.h, 32 * k, tc_.n, &raw_full[k]);
           }
-        }
-        if (g >= 0) {
-          const int i = g / a.NKC, k = g - i * a.NKC;
-          const TileCoord tc_ = tile_coord(a, i);
-          const int bs = g % a.band_slots;
-          mbar_wait(&band_empty[bs], ((uint32_t)(g / a.band_slots) & 1u) ^ 1u);
-          mbar_arrive_expect_tx(&band_full[bs], (uint32_t)band_bytes);
-          tma_load_4d(band_ring + (size_t)bs * a.band_slot_bytes, tmBand, tc_.x0 + m.oo + kKC * k, tc_.h, 0, tc_.n,
-                      &band_full[bs]);
+        } else {
+          const int slot = g % kRawSlots1;
+          mbar_wait(&raw_empty[slot], ((uint32_t)(g / kRawSlots1) & 1u) ^ 1u);
+          mbar_arrive_expect_tx(&raw_full[slot], (uint32_t)kRawSlot1);
+          tma_load_4d(smem + slot * kRawSlot1, &tmG1, tc_.x0 + m.oo + kKC * k, tc_.h,
+                      a.P - 1 + m.delta - kKC * k - (kKC - 1), tc_.n, &raw_full[slot]);
         }
       }
     }
