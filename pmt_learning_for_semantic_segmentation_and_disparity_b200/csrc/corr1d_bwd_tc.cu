@@ -10,7 +10,7 @@
 //     128-byte-swizzled [C][32] box per K chunk into a deep ring; raw g into a second ring -- mode 0: the
 //     tile's [P][128] slice as 32-row boxes (a box is recycled for the next tile as soon as its last
 //     chunk is built), mode 1: one [160][32] block per chunk (OOB rows/columns zero-filled by TMA);
-//   * warps 6-13 (builders): re-lay raw g out shared->shared into the swizzled K-major A operand Gd
+//   * warps 6-21 (16 builders): re-lay raw g out shared->shared into the swizzled K-major A operand Gd
 //     (bank-conflict-free LDS/STS); for 3xTF32 they write hi and lo copies and split the landed band;
 //   * warp 1 issues tcgen05.mma kind::tf32 (M=128, N=C, K=8; hi*hi + hi*lo + lo*hi for 3xTF32) into one
 //     of two TMEM accumulators and commits to the mbarriers that recycle the rings;
@@ -27,8 +27,13 @@ constexpr int kTM = 128;                  // output columns per tile (UMMA M)
 constexpr int kKC = 32;                   // band columns per K chunk (4 k-steps of 8)
 constexpr int kGdBytes = kTM * kKC * 4;   // 16 KB: one A-operand chunk
 constexpr int kEpiWarps = 4;
-constexpr int kBuilders = 8;
-constexpr int kThreads = 32 * (3 + kEpiWarps + kBuilders);  // 480: band producer, MMA, 4 epilogue, 8 builders, raw-g producer
+// builder warps: the 3xTF32 build (hi + lo copies, band split) is latency-bound with 2 warps per scheduler, so it
+// gets 16 warps (measured 580 -> 540 us at the headline shape); the plain-TF32 build is lighter and keeps 8.
+template <int kPasses>
+struct BwdCfg {
+  static constexpr int kBuilders = kPasses == 3 ? 16 : 8;
+  static constexpr int kThreads = 32 * (3 + kEpiWarps + kBuilders);  // band producer, MMA, 4 epilogue, builders, raw-g producer
+};
 constexpr int kBox0Bytes = 32 * kTM * 4;          // mode 0: 32 rows of g x 128 columns (16 KB)
 constexpr int kRawRows1 = 160;                    // mode 1: rows of a raw block (>= 128+32-1)
 constexpr int kRawSlot1 = kRawRows1 * kKC * 4;    // 20 KB
@@ -81,10 +86,11 @@ __device__ __forceinline__ TileCoord tile_coord(const TcBwdArgs& a, int i) {
 }
 
 template <int kPasses>
-__global__ void __launch_bounds__(kThreads, 1)
+__global__ void __launch_bounds__(BwdCfg<kPasses>::kThreads, 1)
 corr1d_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmIn1, const __grid_constant__ CUtensorMap tmIn2,
                      const __grid_constant__ CUtensorMap tmG0, const __grid_constant__ CUtensorMap tmG1,
                      float* __restrict__ gin1, float* __restrict__ gin2, const TcBwdArgs a) {
+  constexpr int kBuilders = BwdCfg<kPasses>::kBuilders;
   extern __shared__ __align__(1024) unsigned char smem[];
   uint64_t* band_full = reinterpret_cast<uint64_t*>(smem + a.bar_off);
   uint64_t* band_empty = band_full + kMaxBandSlots;
@@ -225,18 +231,30 @@ corr1d_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmIn1, const __grid_con
       tc::fence_after_sync();
       const bool ok = tc_.x0 + xl < a.W;
       float* o = dst + ((int64_t)tc_.n * a.C * a.H + tc_.h) * (int64_t)a.W + tc_.x0 + xl;
-      for (int cb = 0; cb < a.Cbox && !(a.debug & 8); cb += 32) {
-        float v[32];
-        tc::tmem_ld32(tmem_base + ((uint32_t)(32 * q) << 16) + (uint32_t)(buf * a.acc_cols + cb), v);
-        if (kPasses == 3) {
-          float v2[32];
-          tc::tmem_ld32(tmem_base + ((uint32_t)(32 * q) << 16) + (uint32_t)(buf * a.acc_cols + a.Cbox + cb), v2);
+      if (kPasses == 3) {
+        // 16 columns at a time (keeps registers low with 16 builder warps): D = block0 + block1 (the A_hi*B_lo part)
+        for (int cb = 0; cb < a.Cbox && !(a.debug & 8); cb += 16) {
+          float v[16];
+          const uint32_t t0 = tmem_base + ((uint32_t)(32 * q) << 16) + (uint32_t)(buf * a.acc_cols + cb);
+          tc::tmem_ld16(t0, v);
+          {
+            float v2[16];
+            tc::tmem_ld16(t0 + (uint32_t)a.Cbox, v2);
 #pragma unroll
-          for (int cc = 0; cc < 32; ++cc) v[cc] += v2[cc];
+            for (int cc = 0; cc < 16; ++cc) v[cc] += v2[cc];
+          }
+#pragma unroll
+          for (int cc = 0; cc < 16; ++cc)
+            if (ok && cb + cc < a.C) o[(int64_t)(cb + cc) * pstride] = v[cc];
         }
+      } else {
+        for (int cb = 0; cb < a.Cbox && !(a.debug & 8); cb += 32) {
+          float v[32];
+          tc::tmem_ld32(tmem_base + ((uint32_t)(32 * q) << 16) + (uint32_t)(buf * a.acc_cols + cb), v);
 #pragma unroll
-        for (int cc = 0; cc < 32; ++cc)
-          if (ok && cb + cc < a.C) o[(int64_t)(cb + cc) * pstride] = v[cc];
+          for (int cc = 0; cc < 32; ++cc)
+            if (ok && cb + cc < a.C) o[(int64_t)(cb + cc) * pstride] = v[cc];
+        }
       }
       tc::fence_before_sync();
       __syncwarp();
@@ -244,7 +262,7 @@ corr1d_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmIn1, const __grid_con
     }
   } else {
     // ===== builder warps =====
-    const int bw = wid - 2 - kEpiWarps;  // 0..7
+    const int bw = wid - 2 - kEpiWarps;  // 0..kBuilders-1
     int g = 0;
     for (int i = 0; i < n_my; ++i) {
       int boxes_ready = 0;
@@ -258,9 +276,8 @@ corr1d_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmIn1, const __grid_con
           mbar_wait(&gd_empty[gs], ((uint32_t)(g / a.gd_slots) & 1u) ^ 1u);
           const float* Gt = reinterpret_cast<const float*>(smem);
 #pragma unroll
-          for (int it = 0; it < 4; ++it) {
+          for (int task = bw; task < 32; task += kBuilders) {   // 32 warp tasks per chunk: (16-byte column c4, 32-row block xb)
             if (a.debug & 4) break;
-            const int task = bw + kBuilders * it;   // 32 warp tasks per chunk: (16-byte column c4, 32-row block xb)
             const int c4 = task & 7, xb = task >> 3;
             const int xl = 32 * xb + lane;
             const int pb = kKC * k + 4 * c4 - m.delta - xl;  // p of column jj = 4*c4 + t is pb + t
@@ -294,9 +311,8 @@ corr1d_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmIn1, const __grid_con
           mbar_wait(&gd_empty[gs], ((uint32_t)(g / a.gd_slots) & 1u) ^ 1u);
           const float* raw = reinterpret_cast<const float*>(smem + slot * kRawSlot1);
 #pragma unroll
-          for (int it = 0; it < 4; ++it) {
+          for (int r = bw; r < 32; r += kBuilders) {            // 32 warp tasks per chunk: 4 rows x 32 columns (lane = column)
             if (a.debug & 4) break;
-            const int r = bw + kBuilders * it;      // 32 warp tasks per chunk: 4 rows x 32 columns (lane = column)
 #pragma unroll
             for (int t = 0; t < 4; ++t) {
               const int xl = 4 * r + t;
@@ -361,6 +377,7 @@ int fill_args(TcBwdArgs* a, int C, int H, int W, int P, int passes) {
   a->band_lo_off = a->Cbox * 128;
   a->band_slot_bytes = a->Cbox * 128 * mult;
   a->gd_slots = passes == 3 ? 2 : 3;
+  if (const char* e = getenv("PMT_GD_SLOTS")) a->gd_slots = atoi(e);  // tuning knob
   const int left = 227 * 1024 - 1024 - raw_bytes - a->gd_slots * a->gd_slot_bytes;
   int bslots = left / a->band_slot_bytes;
   if (bslots > kMaxBandSlots) bslots = kMaxBandSlots;
@@ -406,10 +423,10 @@ int launch_corr1d_bwd_tc(const float* in1, const float* in2, const float* gout, 
   const int64_t gx = tiles < per_mode ? tiles : per_mode;
   if (passes == 3) {
     PMT_CUDA_OK(cudaFuncSetAttribute(corr1d_bwd_tc_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
-    corr1d_bwd_tc_kernel<3><<<dim3((unsigned)gx, 2), kThreads, smem_bytes, st>>>(tm1, tm2, tmG0, tmG1, gin1, gin2, a);
+    corr1d_bwd_tc_kernel<3><<<dim3((unsigned)gx, 2), BwdCfg<3>::kThreads, smem_bytes, st>>>(tm1, tm2, tmG0, tmG1, gin1, gin2, a);
   } else {
     PMT_CUDA_OK(cudaFuncSetAttribute(corr1d_bwd_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
-    corr1d_bwd_tc_kernel<1><<<dim3((unsigned)gx, 2), kThreads, smem_bytes, st>>>(tm1, tm2, tmG0, tmG1, gin1, gin2, a);
+    corr1d_bwd_tc_kernel<1><<<dim3((unsigned)gx, 2), BwdCfg<1>::kThreads, smem_bytes, st>>>(tm1, tm2, tmG0, tmG1, gin1, gin2, a);
   }
   PMT_LAUNCH_OK("corr1d_bwd_tc_kernel");
   return PMT_OK;

@@ -16,7 +16,7 @@ if [ "${1:-}" = "ncu" ]; then
   timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 60 --csv --log-file gpurun_out/launches.csv \
       python bench.py --steps 5 --warmup 3 > gpurun_out/ncu_launch.log 2>&1; echo "ncu launches rc=$?"
   echo "== ncu full"
-  timeout 1200 ncu --set full --clock-control none --import-source on -k regex:corr1d -s 6 -c 4 -o gpurun_out/prof \
+  timeout 1200 ncu --set full --clock-control none --import-source on -k regex:corr1d -s 8 -c 2 -o gpurun_out/prof \
       python bench.py --steps 5 --warmup 3 > gpurun_out/ncu_full.log 2>&1; echo "ncu full rc=$?"
   tail -3 gpurun_out/ncu_full.log
 fi
