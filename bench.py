@@ -33,6 +33,10 @@ PAIRS_PER_GPU = 4
 METRIC = "cost-volume fwd+bwd pairs/s @256x512 D=192"
 UNIT = "pairs/s"
 N_SETS = 2  # rotating buffer sets (each 1.34 GB >> 126 MB L2)
+# dram__bytes_read.sum + dram__bytes_write.sum of one launch of the dominant kernel at this exact workload, from the
+# committed ncu --set full capture (per launch; the kernel reads g once per gradient, hence > algorithmic bytes)
+NCU_DRAM_BYTES_BWD = 697_763_840 + 256_311_040
+NCU_SOURCE = "profiles/r01_ncu_corr_tc_v3.md (ncu --set full, corr1d_bwd_tc_kernel<3>, B=4 headline workload)"
 
 
 def algorithmic_work(c=C, h=H, w=W, p=P):
@@ -311,7 +315,8 @@ def run_ours(args, world):
     tf_bwd = 2 * tiles * (128 * 64 * 320 * 2) * 3 * 1e-12      # TFLOP per pair, both gradients
     tf_fwd = tiles * (128 * 320 * 64 * 2) * 3 * 1e-12
     roofline = {"bound": "hbm", "kernel": "corr1d_bwd_tc_kernel<3>", "achieved": bwd_gbs, "peak": hbm_peak, "unit": "GB/s",
-                "frac": bwd_gbs / hbm_peak, "traffic": None, "peak_source": peak_src,
+                "frac": bwd_gbs / hbm_peak, "traffic": NCU_DRAM_BYTES_BWD, "traffic_source": NCU_SOURCE,
+                "peak_source": peak_src,
                 "ms_per_launch": ms_bwd, "algorithmic_bytes_per_launch": B * work["bytes_bwd"],
                 "note": "default engine = tcgen05 tensor cores with the 3xTF32 split (fp32-accurate); tensor FLOPs are "
                         "cheap enough that the op is HBM-bound; the CUDA-core (fp32 FFMA) engine is reported beside it",
