@@ -6,7 +6,7 @@
  *   - plain pointers and sizes only; no torch types.  Every pointer is a DEVICE pointer to a dense
  *     row-major fp32 tensor unless its name ends in `_host`.
  *   - the caller owns every buffer; the library never allocates, frees or retains device memory
- *     (the `_host` convenience entry points allocate and free their own scratch inside the call).
+ *     (exception: the `_host` convenience entry point keeps a grow-only per-device scratch + streams).
  *   - `stream` is a cudaStream_t passed as void*; kernels are only enqueued, never synchronised
  *     (the `_host` entry points synchronise before returning because they hand back host data).
  *   - return value 0 = success; non-zero = error, message via pmt_last_error() (thread-local).
@@ -128,8 +128,8 @@ int pmt_warp1d_bwd_f32(const float* img, const float* off, const float* gout, fl
  * Host-buffer entry point for the headline workload (what a non-PyTorch caller of the reference's
  * sampler backend would bind): forward + backward of the 1 x P correlation on HOST tensors.
  * Copies in (in1,in2,gout), runs both kernels, copies out (out,gin1,gin2), batch item by batch
- * item on two streams so copies overlap compute, then synchronises.  Host buffers should be
- * pinned for full PCIe rate.  Returns 0 on success.
+ * item through 3 device slots with separate H2D / compute / D2H streams (both PCIe directions and
+ * the kernels overlap), then synchronises.  Host buffers should be pinned for full PCIe rate.
  * ------------------------------------------------------------------------------------------- */
 int pmt_corr1d_fwd_bwd_host_f32(const float* in1_host, const float* in2_host, const float* gout_host,
                                 float* out_host, float* gin1_host, float* gin2_host, int B, int C,
@@ -142,6 +142,8 @@ int pmt_corr1d_fwd_bwd_host_f32(const float* in1_host, const float* in2_host, co
  * of `bytes` bytes src->dst with a float4 grid-stride kernel, returns GB/s (read+write).
  * ------------------------------------------------------------------------------------------- */
 int pmt_probe_fp32_fma(int iters, double* tflops, void* stream);
+/* development hook (profiling builds only): which=0 sets the device buffer for per-role wait-cycle counters */
+int pmt_debug_set_ptr(int which, void* p);
 int pmt_probe_copy(const void* src, void* dst, int64_t bytes, double* gbps, void* stream);
 
 #ifdef __cplusplus

@@ -4,6 +4,8 @@
 #include <stdarg.h>
 #include <string.h>
 
+#include <mutex>
+
 #include "common.cuh"
 
 namespace pmt {
@@ -33,6 +35,8 @@ int launch_dispreg_bwd(const float*, float*, int, int, int, int, cudaStream_t);
 int launch_warp_fwd(const float*, const float*, float*, int, int, int, int, int, cudaStream_t);
 int launch_warp_bwd(const float*, const float*, const float*, float*, float*, int, int, int, int, int,
                     cudaStream_t);
+
+extern long long* g_bwd_prof;  // corr1d_bwd_tc.cu (profiling builds)
 
 // ---- error text ---------------------------------------------------------------------------------
 static thread_local char g_err[512] = "";
@@ -312,49 +316,79 @@ int pmt_warp1d_bwd_f32(const float* img, const float* off, const float* gout, fl
   return launch_warp_bwd(img, off, gout, gimg, goff, N, C, H, W, gout_cnhw, static_cast<cudaStream_t>(stream));
 }
 
-// Host-buffer forward+backward of the 1 x P correlation, one batch item per pipeline slot.
+// Host-buffer forward+backward of the 1 x P correlation.  Batch items flow through kSlots device slots; each slot
+// has its own H2D, compute and D2H stream so the three directions of consecutive items overlap (PCIe is full
+// duplex).  The device scratch and the streams are cached per device and reused by later calls (grow-only), so a
+// steady-state call performs no allocation.
+namespace {
+struct HostPipe {
+  static constexpr int kSlots = 3;
+  cudaStream_t h2d[kSlots] = {}, run[kSlots] = {}, d2h[kSlots] = {};
+  cudaEvent_t in_done[kSlots] = {}, run_done[kSlots] = {}, out_done[kSlots] = {};
+  float* buf[kSlots] = {};
+  size_t cap = 0;  // elements per slot
+  bool ready = false;
+};
+HostPipe g_pipes[64];
+std::mutex g_pipe_mu;
+}  // namespace
+
 int pmt_corr1d_fwd_bwd_host_f32(const float* in1_h, const float* in2_h, const float* gout_h, float* out_h,
                                 float* gin1_h, float* gin2_h, int B, int C, int H, int W, int P, int dilp) {
   PMT_CHECK_ARG(in1_h && in2_h && gout_h && out_h && gin1_h && gin2_h, "host corr: null pointer");
   PMT_CHECK_ARG(B >= 0 && C >= 1 && H >= 1 && W >= 1 && P >= 1 && dilp >= 1, "host corr: bad dimension");
+  int dev = 0;
+  PMT_CUDA_OK(cudaGetDevice(&dev));
+  PMT_CHECK_ARG(dev >= 0 && dev < 64, "host corr: device index out of range");
+  std::lock_guard<std::mutex> lock(g_pipe_mu);
+  HostPipe& hp = g_pipes[dev];
   const size_t fe = (size_t)C * H * W, oe = (size_t)P * H * W;
-  constexpr int kSlots = 2;
-  cudaStream_t st[kSlots] = {nullptr, nullptr};
-  float* buf[kSlots] = {nullptr, nullptr};
-  int rc = PMT_OK;
-  auto fail = [&](cudaError_t e, const char* what) {
-    set_error("host corr: %s failed: %s", what, cudaGetErrorString(e));
-    rc = PMT_ERR_CUDA;
-  };
   const size_t slot_elems = 4 * fe + 2 * oe;  // in1,in2,gin1,gin2 | gout,out
-  for (int s = 0; s < kSlots && rc == PMT_OK; ++s) {
-    cudaError_t e = cudaStreamCreateWithFlags(&st[s], cudaStreamNonBlocking);
-    if (e != cudaSuccess) { fail(e, "cudaStreamCreate"); break; }
-    e = cudaMalloc(&buf[s], slot_elems * sizeof(float));
-    if (e != cudaSuccess) { fail(e, "cudaMalloc"); break; }
-  }
-  for (int n = 0; n < B && rc == PMT_OK; ++n) {
-    const int s = n % kSlots;
-    float *d1 = buf[s], *d2 = d1 + fe, *g1 = d2 + fe, *g2 = g1 + fe, *dg = g2 + fe, *dout = dg + oe;
-    cudaError_t e;
-    if ((e = cudaMemcpyAsync(d1, in1_h + n * fe, fe * 4, cudaMemcpyHostToDevice, st[s])) != cudaSuccess) { fail(e, "H2D in1"); break; }
-    if ((e = cudaMemcpyAsync(d2, in2_h + n * fe, fe * 4, cudaMemcpyHostToDevice, st[s])) != cudaSuccess) { fail(e, "H2D in2"); break; }
-    if ((e = cudaMemcpyAsync(dg, gout_h + n * oe, oe * 4, cudaMemcpyHostToDevice, st[s])) != cudaSuccess) { fail(e, "H2D gout"); break; }
-    if ((rc = pmt_corr1d_fwd_f32(d1, d2, dout, 1, C, H, W, P, dilp, st[s])) != PMT_OK) break;
-    if ((rc = pmt_corr1d_bwd_f32(d1, d2, dg, g1, g2, 1, C, H, W, P, dilp, st[s])) != PMT_OK) break;
-    if ((e = cudaMemcpyAsync(out_h + n * oe, dout, oe * 4, cudaMemcpyDeviceToHost, st[s])) != cudaSuccess) { fail(e, "D2H out"); break; }
-    if ((e = cudaMemcpyAsync(gin1_h + n * fe, g1, fe * 4, cudaMemcpyDeviceToHost, st[s])) != cudaSuccess) { fail(e, "D2H gin1"); break; }
-    if ((e = cudaMemcpyAsync(gin2_h + n * fe, g2, fe * 4, cudaMemcpyDeviceToHost, st[s])) != cudaSuccess) { fail(e, "D2H gin2"); break; }
-  }
-  for (int s = 0; s < kSlots; ++s) {
-    if (st[s]) {
-      cudaError_t e = cudaStreamSynchronize(st[s]);
-      if (e != cudaSuccess && rc == PMT_OK) fail(e, "cudaStreamSynchronize");
-      cudaStreamDestroy(st[s]);
+  if (!hp.ready) {
+    for (int s = 0; s < HostPipe::kSlots; ++s) {
+      PMT_CUDA_OK(cudaStreamCreateWithFlags(&hp.h2d[s], cudaStreamNonBlocking));
+      PMT_CUDA_OK(cudaStreamCreateWithFlags(&hp.run[s], cudaStreamNonBlocking));
+      PMT_CUDA_OK(cudaStreamCreateWithFlags(&hp.d2h[s], cudaStreamNonBlocking));
+      PMT_CUDA_OK(cudaEventCreateWithFlags(&hp.in_done[s], cudaEventDisableTiming));
+      PMT_CUDA_OK(cudaEventCreateWithFlags(&hp.run_done[s], cudaEventDisableTiming));
+      PMT_CUDA_OK(cudaEventCreateWithFlags(&hp.out_done[s], cudaEventDisableTiming));
     }
-    if (buf[s]) cudaFree(buf[s]);
+    hp.ready = true;
   }
-  return rc;
+  if (slot_elems > hp.cap) {
+    for (int s = 0; s < HostPipe::kSlots; ++s) {
+      if (hp.buf[s]) cudaFree(hp.buf[s]);
+      hp.buf[s] = nullptr;
+      PMT_CUDA_OK(cudaMalloc(&hp.buf[s], slot_elems * sizeof(float)));
+    }
+    hp.cap = slot_elems;
+  }
+  for (int n = 0; n < B; ++n) {
+    const int s = n % HostPipe::kSlots;
+    float *d1 = hp.buf[s], *d2 = d1 + fe, *g1 = d2 + fe, *g2 = g1 + fe, *dg = g2 + fe, *dout = dg + oe;
+    // the slot is free again once the previous item's results have left it
+    PMT_CUDA_OK(cudaStreamWaitEvent(hp.h2d[s], hp.out_done[s], 0));
+    PMT_CUDA_OK(cudaMemcpyAsync(d1, in1_h + n * fe, fe * 4, cudaMemcpyHostToDevice, hp.h2d[s]));
+    PMT_CUDA_OK(cudaMemcpyAsync(d2, in2_h + n * fe, fe * 4, cudaMemcpyHostToDevice, hp.h2d[s]));
+    PMT_CUDA_OK(cudaMemcpyAsync(dg, gout_h + n * oe, oe * 4, cudaMemcpyHostToDevice, hp.h2d[s]));
+    PMT_CUDA_OK(cudaEventRecord(hp.in_done[s], hp.h2d[s]));
+    PMT_CUDA_OK(cudaStreamWaitEvent(hp.run[s], hp.in_done[s], 0));
+    if (int rc = pmt_corr1d_fwd_f32(d1, d2, dout, 1, C, H, W, P, dilp, hp.run[s])) return rc;
+    if (int rc = pmt_corr1d_bwd_f32(d1, d2, dg, g1, g2, 1, C, H, W, P, dilp, hp.run[s])) return rc;
+    PMT_CUDA_OK(cudaEventRecord(hp.run_done[s], hp.run[s]));
+    PMT_CUDA_OK(cudaStreamWaitEvent(hp.d2h[s], hp.run_done[s], 0));
+    PMT_CUDA_OK(cudaMemcpyAsync(out_h + n * oe, dout, oe * 4, cudaMemcpyDeviceToHost, hp.d2h[s]));
+    PMT_CUDA_OK(cudaMemcpyAsync(gin1_h + n * fe, g1, fe * 4, cudaMemcpyDeviceToHost, hp.d2h[s]));
+    PMT_CUDA_OK(cudaMemcpyAsync(gin2_h + n * fe, g2, fe * 4, cudaMemcpyDeviceToHost, hp.d2h[s]));
+    PMT_CUDA_OK(cudaEventRecord(hp.out_done[s], hp.d2h[s]));
+  }
+  for (int s = 0; s < HostPipe::kSlots; ++s) PMT_CUDA_OK(cudaStreamSynchronize(hp.d2h[s]));
+  return PMT_OK;
+}
+
+int pmt_debug_set_ptr(int which, void* p) {
+  if (which == 0) pmt::g_bwd_prof = static_cast<long long*>(p);
+  return PMT_OK;
 }
 
 int pmt_probe_fp32_fma(int iters, double* tflops, void* stream) {

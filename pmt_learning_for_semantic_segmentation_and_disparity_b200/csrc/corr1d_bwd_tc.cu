@@ -32,6 +32,10 @@ constexpr int kEpiWarps = 4;
 template <int kPasses>
 struct BwdCfg {
   static constexpr int kBuilders = kPasses == 3 ? 16 : 8;
+  // Every builder warp pays a fixed latency chain per chunk (barrier waits, tcgen05.st / fence, arrive), so the
+  // builders are split into two groups that take alternate chunks: the chain is paid every other chunk.
+  static constexpr int kGroups = 2;
+  static constexpr int kGroupWarps = kBuilders / kGroups;
   static constexpr int kThreads = 32 * (3 + kEpiWarps + kBuilders);  // band producer, MMA, 4 epilogue, builders, raw-g producer
 };
 constexpr int kBox0Bytes = 32 * kTM * 4;          // mode 0: 32 rows of g x 128 columns (16 KB)
@@ -44,6 +48,10 @@ struct TcBwdMode {
   int oo;      // band column j <-> image column x0 + oo + j  (multiple of 4)
   int delta;
   int koff;    // mode 0: box b of the g slice is last used by chunk min(NKC-1, b + koff)
+  int a_slots;     // A-operand ring depth (smem Gd slots, or TMEM slots when tmem_a)
+  int band_slots;  // band ring depth
+  int band_off;    // byte offset of the band ring
+  int tmem_a;      // 1: Gd chunks are written straight into TMEM (tcgen05.st) and the MMA takes A from TMEM
 };
 
 struct TcBwdArgs {
@@ -52,10 +60,10 @@ struct TcBwdArgs {
   int NKC;             // K chunks per tile
   int n_xtiles, n_tiles;
   int n_gboxes;        // mode 0: 32-row boxes of the resident g slice (= raw ring slots)
-  int gd_slots, band_slots;
+  int a_base, aslot_cols;  // TMEM A ring: first column, columns per slot (32 hi [+ 32 lo])
   int gd_slot_bytes, gd_lo_off;       // Gd ring slot: hi [16 KB] (+ lo [16 KB])
   int band_slot_bytes, band_lo_off;   // band ring slot: hi [Cbox*128] (+ lo)
-  int gd_off, band_off, bar_off;      // byte offsets in dynamic shared memory (raw ring at 0)
+  int gd_off, bar_off;                // byte offsets in dynamic shared memory (raw ring at 0)
   int tmem_cols;
   int acc_cols;        // TMEM columns per accumulator (Cbox, or 2*Cbox for 3xTF32: hi and lo column blocks)
   TcBwdMode m[2];
@@ -73,6 +81,18 @@ __device__ __forceinline__ float lo_tf32(float x) {
   return x - __uint_as_float(__float_as_uint(x) & 0xffffe000u);
 }
 
+// Optional per-role wait profiling (PMT_TC_DEBUG bit 1024): cycles spent blocked on each barrier family, per warp.
+#ifdef PMT_BWD_PROFILE
+#define PWAIT(slot, bar, par)                      \
+  do {                                             \
+    const long long _t0 = clock64();               \
+    mbar_wait(bar, par);                           \
+    wait_cyc[slot] += clock64() - _t0;             \
+  } while (0)
+#else
+#define PWAIT(slot, bar, par) mbar_wait(bar, par)
+#endif
+
 struct TileCoord {
   int x0, h, n;
 };
@@ -89,8 +109,10 @@ template <int kPasses>
 __global__ void __launch_bounds__(BwdCfg<kPasses>::kThreads, 1)
 corr1d_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmIn1, const __grid_constant__ CUtensorMap tmIn2,
                      const __grid_constant__ CUtensorMap tmG0, const __grid_constant__ CUtensorMap tmG1,
-                     float* __restrict__ gin1, float* __restrict__ gin2, const TcBwdArgs a) {
+                     float* __restrict__ gin1, float* __restrict__ gin2, const TcBwdArgs a,
+                     long long* __restrict__ prof) {
   constexpr int kBuilders = BwdCfg<kPasses>::kBuilders;
+  constexpr int kGroupWarps = BwdCfg<kPasses>::kGroupWarps;
   extern __shared__ __align__(1024) unsigned char smem[];
   uint64_t* band_full = reinterpret_cast<uint64_t*>(smem + a.bar_off);
   uint64_t* band_empty = band_full + kMaxBandSlots;
@@ -102,14 +124,18 @@ corr1d_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmIn1, const __grid_con
   uint64_t* tmem_empty = tmem_full + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
   unsigned char* gd_ring = smem + a.gd_off;
-  unsigned char* band_ring = smem + a.band_off;
 
   const int mode = blockIdx.y;
   const TcBwdMode m = a.m[mode];
+  unsigned char* band_ring = smem + m.band_off;
   const CUtensorMap* tmBand = mode == 0 ? &tmIn2 : &tmIn1;
   float* __restrict__ dst = mode == 0 ? gin1 : gin2;
 
   const int tid = threadIdx.x, wid = tid >> 5, lane = tid & 31;
+#ifdef PMT_BWD_PROFILE
+  long long wait_cyc[4] = {0, 0, 0, 0};
+  const long long t_start = clock64();
+#endif
   const int band_bytes = a.Cbox * 128;
   const int n_my = (a.n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;  // tiles of this CTA
   const int G = n_my * a.NKC;                                                            // chunks of this CTA
@@ -120,12 +146,12 @@ corr1d_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmIn1, const __grid_con
       mbar_init(&band_empty[s], 1);
     }
     for (int s = 0; s < kMaxGdSlots; ++s) {
-      mbar_init(&gd_built[s], kBuilders);
+      mbar_init(&gd_built[s], kGroupWarps);
       mbar_init(&gd_empty[s], 1);
     }
     for (int s = 0; s < 8; ++s) {
       mbar_init(&raw_full[s], 1);
-      mbar_init(&raw_empty[s], kBuilders);
+      mbar_init(&raw_empty[s], blockIdx.y == 0 ? kBuilders : kGroupWarps);
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tmem_full[s], 1);
@@ -146,14 +172,17 @@ corr1d_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmIn1, const __grid_con
     // ===== TMA producer 1: the feature band, one swizzled [C][32] box per K chunk, ring spans tile boundaries =====
     if (lane == 0) {
       tma_prefetch_desc(tmBand);
-      for (int g = 0; g < G; ++g) {
-        const int i = g / a.NKC, k = g - i * a.NKC;
+      int bs = 0;
+      uint32_t bph = 1;  // parity to wait for on band_empty (first pass over the ring is free)
+      for (int i = 0; i < n_my; ++i) {
         const TileCoord tc_ = tile_coord(a, i);
-        const int bs = g % a.band_slots;
-        mbar_wait(&band_empty[bs], ((uint32_t)(g / a.band_slots) & 1u) ^ 1u);
-        mbar_arrive_expect_tx(&band_full[bs], (uint32_t)band_bytes);
-        tma_load_4d(band_ring + (size_t)bs * a.band_slot_bytes, tmBand, tc_.x0 + m.oo + kKC * k, tc_.h, 0, tc_.n,
-                    &band_full[bs]);
+        for (int k = 0; k < a.NKC; ++k) {
+          PWAIT(0, &band_empty[bs], bph);
+          mbar_arrive_expect_tx(&band_full[bs], (uint32_t)band_bytes);
+          tma_load_4d(band_ring + (size_t)bs * a.band_slot_bytes, tmBand, tc_.x0 + m.oo + kKC * k, tc_.h, 0, tc_.n,
+                      &band_full[bs]);
+          if (++bs == m.band_slots) bs = 0, bph ^= 1u;
+        }
       }
     }
   } else if (wid == 2 + kEpiWarps + kBuilders) {
@@ -161,60 +190,90 @@ corr1d_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmIn1, const __grid_con
     // reloaded for the next tile as soon as the builders release it; mode 1: one [160][32] block per chunk.  It
     // only waits on slot releases from the builders, so it runs as far ahead as the ring allows. =====
     if (lane == 0) {
-      for (int g = 0; g < G; ++g) {
-        const int i = g / a.NKC, k = g - i * a.NKC;
+      int slot = 0;
+      uint32_t sph = 1;  // mode 1: parity to wait for on raw_empty[slot]
+      for (int i = 0; i < n_my; ++i) {
         const TileCoord tc_ = tile_coord(a, i);
-        if (mode == 0) {
-          if (k < a.n_gboxes) {
-            mbar_wait(&raw_empty[k], ((uint32_t)i & 1u) ^ 1u);  // previous tile is done with this box
-            mbar_arrive_expect_tx(&raw_full[k], (uint32_t)kBox0Bytes);
-            tma_load_4d(smem + k * kBox0Bytes, &tmG0, tc_.x0, tc_.h, 32 * k, tc_.n, &raw_full[k]);
+        const bool more = !(a.debug & 512) && i + 1 < n_my;
+        const TileCoord nx = tile_coord(a, more ? i + 1 : i);
+        for (int k = 0; k < a.NKC; ++k) {
+          if (mode == 0) {
+            if (k < a.n_gboxes) {
+              // the smem ring only reaches about one tile ahead: pull the next tile's box into L2 now
+              if (more) tma_prefetch_l2_4d(&tmG0, nx.x0, nx.h, 32 * k, nx.n);
+              PWAIT(0, &raw_empty[k], ((uint32_t)i & 1u) ^ 1u);  // previous tile is done with this box
+              mbar_arrive_expect_tx(&raw_full[k], (uint32_t)kBox0Bytes);
+              tma_load_4d(smem + k * kBox0Bytes, &tmG0, tc_.x0, tc_.h, 32 * k, tc_.n, &raw_full[k]);
+            }
+          } else {
+            const int p0 = a.P - 1 + m.delta - kKC * k - (kKC - 1);
+            if (more) tma_prefetch_l2_4d(&tmG1, nx.x0 + m.oo + kKC * k, nx.h, p0, nx.n);
+            PWAIT(0, &raw_empty[slot], sph);
+            mbar_arrive_expect_tx(&raw_full[slot], (uint32_t)kRawSlot1);
+            tma_load_4d(smem + slot * kRawSlot1, &tmG1, tc_.x0 + m.oo + kKC * k, tc_.h, p0, tc_.n, &raw_full[slot]);
+            if (++slot == kRawSlots1) slot = 0, sph ^= 1u;
           }
-        } else {
-          const int slot = g % kRawSlots1;
-          mbar_wait(&raw_empty[slot], ((uint32_t)(g / kRawSlots1) & 1u) ^ 1u);
-          mbar_arrive_expect_tx(&raw_full[slot], (uint32_t)kRawSlot1);
-          tma_load_4d(smem + slot * kRawSlot1, &tmG1, tc_.x0 + m.oo + kKC * k, tc_.h,
-                      a.P - 1 + m.delta - kKC * k - (kKC - 1), tc_.n, &raw_full[slot]);
         }
       }
     }
   } else if (wid == 1) {
     // ===== MMA issuer =====
+    // One thread issues everything, so its instruction count per chunk is on the critical path (measured: with
+    // div/mod slot arithmetic and full descriptor rebuilds it was busy 92% of the time while the tensor pipe idled).
+    // Slots and phases are kept as running counters and descriptors are advanced by adding to their low word.
     if (lane == 0) {
       const uint32_t idesc = tc::make_idesc(2, 0, 0, kTM, a.Cbox);
       const uint32_t idesc2 = tc::make_idesc(2, 0, 0, kTM, 2 * a.Cbox);  // B = [band_hi ; band_lo] stacked along N
-      int g = 0;
+      const uint64_t dA0 = tc::smem_desc(smem_u32(gd_ring), 16, 1024, 2);
+      const uint64_t dB0 = tc::smem_desc(smem_u32(band_ring), 16, 1024, 2);
+      const uint32_t a_step = (uint32_t)a.gd_slot_bytes >> 4, b_step = (uint32_t)a.band_slot_bytes >> 4;
+      const uint32_t a_lo = (uint32_t)a.gd_lo_off >> 4;
+      const bool tmem_a = m.tmem_a != 0, skip = (a.debug & 16) != 0;
+      int gs = 0, bs = 0;
+      uint32_t gph = 0, bph = 0;
       for (int i = 0; i < n_my; ++i) {
         const int buf = i & 1;
-        mbar_wait(&tmem_empty[buf], ((uint32_t)(i >> 1) & 1u) ^ 1u);  // epilogue drained this accumulator
+        PWAIT(0, &tmem_empty[buf], ((uint32_t)(i >> 1) & 1u) ^ 1u);  // epilogue drained this accumulator
         tc::fence_after_sync();
         const uint32_t d_tmem = tmem_base + (uint32_t)(buf * a.acc_cols);
-        for (int k = 0; k < a.NKC; ++k, ++g) {
-          const int gs = g % a.gd_slots, bs = g % a.band_slots;
-          mbar_wait(&gd_built[gs], (uint32_t)(g / a.gd_slots) & 1u);
-          if (kPasses == 1) mbar_wait(&band_full[bs], (uint32_t)(g / a.band_slots) & 1u);
+        for (int k = 0; k < a.NKC; ++k) {
+          PWAIT(1, &gd_built[gs], gph);
+          if (kPasses == 1) PWAIT(2, &band_full[bs], bph);
           tc::fence_after_sync();
-          const uint32_t sa = smem_u32(gd_ring + (size_t)gs * a.gd_slot_bytes);
-          const uint32_t sb = smem_u32(band_ring + (size_t)bs * a.band_slot_bytes);
+          const uint64_t dB = dB0 + (uint64_t)(b_step * (uint32_t)bs);
+          if (!skip) {
+            if (tmem_a) {
+              const uint32_t ta = tmem_base + (uint32_t)(a.a_base + gs * a.aslot_cols);
 #pragma unroll
-          for (int kk = 0; kk < kKC / 8; ++kk) {
-            if (a.debug & 16) break;
-            const uint32_t acc = (k > 0 || kk > 0) ? 1u : 0u;
-            const uint64_t dA = tc::smem_desc(sa + kk * 32, 16, 1024, 2);
-            const uint64_t dB = tc::smem_desc(sb + kk * 32, 16, 1024, 2);
-            if (kPasses == 3) {
-              // D[:, 0:C] += A_hi*B_hi + A_lo*B_hi ; D[:, C:2C] += A_hi*B_lo  (A_hi is read once for both B halves;
-              // the epilogue adds the two column blocks)
-              const uint64_t dAl = tc::smem_desc(sa + a.gd_lo_off + kk * 32, 16, 1024, 2);
-              tc::mma_tf32(d_tmem, dA, dB, idesc2, acc);
-              tc::mma_tf32(d_tmem, dAl, dB, idesc, 1u);
+              for (int kk = 0; kk < kKC / 8; ++kk) {
+                const uint32_t acc = (k > 0 || kk > 0) ? 1u : 0u;
+                if (kPasses == 3) {
+                  tc::mma_tf32_ts(d_tmem, ta + 8 * kk, dB + 2 * kk, idesc2, acc);
+                  tc::mma_tf32_ts(d_tmem, ta + 32 + 8 * kk, dB + 2 * kk, idesc, 1u);
+                } else {
+                  tc::mma_tf32_ts(d_tmem, ta + 8 * kk, dB + 2 * kk, idesc, acc);
+                }
+              }
             } else {
-              tc::mma_tf32(d_tmem, dA, dB, idesc, acc);
+              const uint64_t dA = dA0 + (uint64_t)(a_step * (uint32_t)gs);
+#pragma unroll
+              for (int kk = 0; kk < kKC / 8; ++kk) {
+                const uint32_t acc = (k > 0 || kk > 0) ? 1u : 0u;
+                if (kPasses == 3) {
+                  // D[:, 0:C] += A_hi*B_hi + A_lo*B_hi ; D[:, C:2C] += A_hi*B_lo  (A_hi is read once for both B
+                  // halves; the epilogue adds the two column blocks)
+                  tc::mma_tf32(d_tmem, dA + 2 * kk, dB + 2 * kk, idesc2, acc);
+                  tc::mma_tf32(d_tmem, dA + a_lo + 2 * kk, dB + 2 * kk, idesc, 1u);
+                } else {
+                  tc::mma_tf32(d_tmem, dA + 2 * kk, dB + 2 * kk, idesc, acc);
+                }
+              }
             }
           }
           tc::mma_commit(&gd_empty[gs]);
           tc::mma_commit(&band_empty[bs]);
+          if (++gs == m.a_slots) gs = 0, gph ^= 1u;
+          if (++bs == m.band_slots) bs = 0, bph ^= 1u;
         }
         tc::mma_commit(&tmem_full[buf]);
       }
@@ -227,7 +286,7 @@ corr1d_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmIn1, const __grid_con
     for (int i = 0; i < n_my; ++i) {
       const int buf = i & 1;
       const TileCoord tc_ = tile_coord(a, i);
-      mbar_wait(&tmem_full[buf], (uint32_t)(i >> 1) & 1u);
+      PWAIT(0, &tmem_full[buf], (uint32_t)(i >> 1) & 1u);
       tc::fence_after_sync();
       const bool ok = tc_.x0 + xl < a.W;
       float* o = dst + ((int64_t)tc_.n * a.C * a.H + tc_.h) * (int64_t)a.W + tc_.x0 + xl;
@@ -262,56 +321,96 @@ corr1d_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmIn1, const __grid_con
     }
   } else {
     // ===== builder warps =====
-    const int bw = wid - 2 - kEpiWarps;  // 0..kBuilders-1
+    const int bw = wid - 2 - kEpiWarps;  // 0..kBuilders-1; consecutive warps cycle through the 4 TMEM lane quarters
+    const int grp = (bw >> 2) & 1;       // chunk parity this warp handles
+    const int gw = ((bw >> 2) >> 1) * 4 + (bw & 3);  // index inside the group, 0..kGroupWarps-1
+    // running ring positions for the chunks this warp visits (g = grp, grp+2, ...): slot, and the phase parity seen
+    // by a consumer-side wait (full/built); producer-side waits (empty) use the opposite parity
     int g = 0;
+    int gs = grp % m.a_slots, bs = grp % m.band_slots, rs = grp % kRawSlots1;
+    uint32_t gph = (uint32_t)(grp / m.a_slots) & 1u, bph = (uint32_t)(grp / m.band_slots) & 1u,
+             rph = (uint32_t)(grp / kRawSlots1) & 1u;
+    auto advance2 = [](int& slot, uint32_t& ph, int n) {
+      slot += 2;
+      if (slot >= n) slot -= n, ph ^= 1u;   // ring sizes are even and >= 2
+    };
     for (int i = 0; i < n_my; ++i) {
       int boxes_ready = 0;
+      int next_rel = 0;                  // mode 0: boxes are handed back to the producer in increasing order
       for (int k = 0; k < a.NKC; ++k, ++g) {
-        const int gs = g % a.gd_slots;
+        if ((g & 1) != grp) continue;
         unsigned char* sa = gd_ring + (size_t)gs * a.gd_slot_bytes;
         if (mode == 0) {
           // rows p <= 32k+31-delta are needed: boxes 0..k of this tile's [P][128] slice
           const int need = (k + 1 < a.n_gboxes) ? k + 1 : a.n_gboxes;
-          while (boxes_ready < need) mbar_wait(&raw_full[boxes_ready++], (uint32_t)i & 1u);
-          mbar_wait(&gd_empty[gs], ((uint32_t)(g / a.gd_slots) & 1u) ^ 1u);
+          while (boxes_ready < need) { PWAIT(0, &raw_full[boxes_ready], (uint32_t)i & 1u); ++boxes_ready; }
+          PWAIT(1, &gd_empty[gs], gph ^ 1u);
           const float* Gt = reinterpret_cast<const float*>(smem);
+          if (m.tmem_a) {
+            // A operand straight into TMEM: thread = Gd row x (TMEM lane), kCols consecutive band columns per warp
+            constexpr int kCols = 32 / (kGroupWarps / 4);
+            static_assert(kCols == 16 || kCols == 32, "group size");
+            const int q = wid & 3, sub = gw >> 2;
+            const int xl = 32 * q + lane;
+            const int pb = kKC * k + sub * kCols - m.delta - xl;  // p of column jj = sub*kCols + t is pb + t
+            const uint32_t ta = tmem_base + ((uint32_t)(32 * q) << 16) + (uint32_t)(a.a_base + gs * a.aslot_cols + sub * kCols);
 #pragma unroll
-          for (int task = bw; task < 32; task += kBuilders) {   // 32 warp tasks per chunk: (16-byte column c4, 32-row block xb)
-            if (a.debug & 4) break;
-            const int c4 = task & 7, xb = task >> 3;
-            const int xl = 32 * xb + lane;
-            const int pb = kKC * k + 4 * c4 - m.delta - xl;  // p of column jj = 4*c4 + t is pb + t
-            float v[4];
+            for (int c0 = 0; c0 < kCols; c0 += 16) {
+              float w[16];
 #pragma unroll
-            for (int t = 0; t < 4; ++t) {
-              const int p = pb + t;
-              v[t] = (p >= 0 && p < a.P) ? Gt[p * kTM + xl] : 0.f;
+              for (int t = 0; t < 16; ++t) {
+                const int p = pb + c0 + t;
+                w[t] = (p >= 0 && p < a.P && !(a.debug & 4)) ? Gt[p * kTM + xl] : 0.f;
+              }
+              tc::tmem_st16(ta + c0, w);
+              if (kPasses == 3) {
+#pragma unroll
+                for (int t = 0; t < 16; ++t) w[t] = lo_tf32(w[t]);
+                tc::tmem_st16(ta + 32 + c0, w);
+              }
             }
-            const uint32_t off = kmajor_off(xl, 4 * c4);
-            *reinterpret_cast<float4*>(sa + off) = make_float4(v[0], v[1], v[2], v[3]);
-            if (kPasses == 3)
-              *reinterpret_cast<float4*>(sa + a.gd_lo_off + off) =
-                  make_float4(lo_tf32(v[0]), lo_tf32(v[1]), lo_tf32(v[2]), lo_tf32(v[3]));
+            tc::tmem_st_wait();
+            tc::fence_before_sync();
+          } else {
+#pragma unroll
+            for (int task = gw; task < 32; task += kGroupWarps) {   // 32 warp tasks per chunk: (16-byte column c4, 32-row block xb)
+              if (a.debug & 4) break;
+              const int c4 = task & 7, xb = task >> 3;
+              const int xl = 32 * xb + lane;
+              const int pb = kKC * k + 4 * c4 - m.delta - xl;  // p of column jj = 4*c4 + t is pb + t
+              float v[4];
+#pragma unroll
+              for (int t = 0; t < 4; ++t) {
+                const int p = pb + t;
+                v[t] = (p >= 0 && p < a.P) ? Gt[p * kTM + xl] : 0.f;
+              }
+              const uint32_t off = kmajor_off(xl, 4 * c4);
+              *reinterpret_cast<float4*>(sa + off) = make_float4(v[0], v[1], v[2], v[3]);
+              if (kPasses == 3)
+                *reinterpret_cast<float4*>(sa + a.gd_lo_off + off) =
+                    make_float4(lo_tf32(v[0]), lo_tf32(v[1]), lo_tf32(v[2]), lo_tf32(v[3]));
+            }
           }
-          // recycle the boxes whose last reader was this chunk (the next tile's loads may land in them)
+          // hand back every box this warp will not read again (it visits chunks k, k+2, ...): box b is last used by
+          // chunk min(NKC-1, b+koff), so it is dead for this warp once k >= that chunk - 1
           __syncwarp();
           if (lane == 0) {
-            if (k < a.NKC - 1) {
-              const int b = k - m.koff;
-              if (b >= 0 && b < a.n_gboxes) mbar_arrive(&raw_empty[b]);
-            } else {
-              int b = a.NKC - 1 - m.koff;
-              if (b < 0) b = 0;
-              for (; b < a.n_gboxes; ++b) mbar_arrive(&raw_empty[b]);
+            const bool last_visit = k + 2 >= a.NKC;
+            while (next_rel < a.n_gboxes) {
+              int kl = next_rel + m.koff;
+              if (kl > a.NKC - 1) kl = a.NKC - 1;
+              if (!(kl <= k + 1 || last_visit)) break;
+              mbar_arrive(&raw_empty[next_rel]);
+              ++next_rel;
             }
           }
         } else {
-          const int slot = g % kRawSlots1;
-          mbar_wait(&raw_full[slot], (uint32_t)(g / kRawSlots1) & 1u);
-          mbar_wait(&gd_empty[gs], ((uint32_t)(g / a.gd_slots) & 1u) ^ 1u);
+          const int slot = rs;
+          PWAIT(0, &raw_full[slot], rph);
+          PWAIT(1, &gd_empty[gs], gph ^ 1u);
           const float* raw = reinterpret_cast<const float*>(smem + slot * kRawSlot1);
 #pragma unroll
-          for (int r = bw; r < 32; r += kBuilders) {            // 32 warp tasks per chunk: 4 rows x 32 columns (lane = column)
+          for (int r = gw; r < 32; r += kGroupWarps) {          // 32 warp tasks per chunk: 4 rows x 32 columns (lane = column)
             if (a.debug & 4) break;
 #pragma unroll
             for (int t = 0; t < 4; ++t) {
@@ -327,11 +426,10 @@ corr1d_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmIn1, const __grid_con
         }
         if (kPasses == 3) {
           // split the landed feature band chunk into hi / lo (position-wise, layout agnostic)
-          const int bs = g % a.band_slots;
-          mbar_wait(&band_full[bs], (uint32_t)(g / a.band_slots) & 1u);
+          PWAIT(2, &band_full[bs], bph);
           unsigned char* sb = band_ring + (size_t)bs * a.band_slot_bytes;
           const int nch = band_bytes / 16;
-          for (int c = (bw * 32 + lane); c < nch && !(a.debug & 32); c += kBuilders * 32) {
+          for (int c = (gw * 32 + lane); c < nch && !(a.debug & 32); c += kGroupWarps * 32) {
             const float4 x = *reinterpret_cast<const float4*>(sb + 16 * c);
             *reinterpret_cast<float4*>(sb + a.band_lo_off + 16 * c) =
                 make_float4(lo_tf32(x.x), lo_tf32(x.y), lo_tf32(x.z), lo_tf32(x.w));
@@ -340,10 +438,20 @@ corr1d_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmIn1, const __grid_con
         fence_proxy_async();
         __syncwarp();
         if (lane == 0) mbar_arrive(&gd_built[gs]);
+        advance2(gs, gph, m.a_slots);
+        advance2(bs, bph, m.band_slots);
+        advance2(rs, rph, kRawSlots1);
       }
     }
   }
 
+#ifdef PMT_BWD_PROFILE
+  if (prof != nullptr && blockIdx.x == 0 && lane == 0) {
+    long long* o = prof + ((size_t)blockIdx.y * 32 + wid) * 5;
+    o[0] = wait_cyc[0], o[1] = wait_cyc[1], o[2] = wait_cyc[2], o[3] = wait_cyc[3];
+    o[4] = clock64() - t_start;
+  }
+#endif
   tc::fence_before_sync();
   __syncthreads();
   if (wid == 1) {
@@ -376,20 +484,42 @@ int fill_args(TcBwdArgs* a, int C, int H, int W, int P, int passes) {
   a->gd_slot_bytes = kGdBytes * mult;
   a->band_lo_off = a->Cbox * 128;
   a->band_slot_bytes = a->Cbox * 128 * mult;
-  a->gd_slots = passes == 3 ? 2 : 3;
-  if (const char* e = getenv("PMT_GD_SLOTS")) a->gd_slots = atoi(e);  // tuning knob
-  const int left = 227 * 1024 - 1024 - raw_bytes - a->gd_slots * a->gd_slot_bytes;
-  int bslots = left / a->band_slot_bytes;
-  if (bslots > kMaxBandSlots) bslots = kMaxBandSlots;
-  if (bslots < 2) return 1;
-  a->band_slots = bslots;
-  a->gd_off = raw_bytes;
-  a->band_off = a->gd_off + a->gd_slots * a->gd_slot_bytes;
-  a->bar_off = a->band_off + a->band_slots * a->band_slot_bytes;
-  a->acc_cols = a->Cbox * (passes == 3 ? 2 : 1);
+  a->acc_cols = a->Cbox * mult;                 // 3xTF32 keeps two column blocks per accumulator
   if (2 * a->acc_cols > 512) return 1;
+  a->gd_off = raw_bytes;
+  const int smem_budget = 227 * 1024 - 1024;
+  // A operand in TMEM (mode 0 only -- its Gd rows are conflict-free column reads of the resident g slice): needs
+  // columns next to the two accumulators.
+  a->aslot_cols = 32 * mult;
+  a->a_base = 2 * a->acc_cols;
+  int tmem_slots = (512 - a->a_base) / a->aslot_cols;
+  if (tmem_slots > kMaxGdSlots) tmem_slots = kMaxGdSlots;
+  tmem_slots &= ~1;                             // even: a slot is always revisited by the same builder group
+  const bool want_tmem_a = getenv("PMT_NO_TMEM_A") == nullptr;
+  int max_end = 0;
+  for (int md = 0; md < 2; ++md) {
+    TcBwdMode& m = a->m[md];
+    m.tmem_a = (md == 0 && want_tmem_a && tmem_slots >= 2) ? 1 : 0;
+    int gd_bytes = 0;
+    if (m.tmem_a) {
+      m.a_slots = tmem_slots;
+    } else {
+      m.a_slots = 2;
+      gd_bytes = m.a_slots * a->gd_slot_bytes;
+    }
+    m.band_off = a->gd_off + gd_bytes;
+    int bslots = (smem_budget - m.band_off) / a->band_slot_bytes;
+    if (bslots > kMaxBandSlots) bslots = kMaxBandSlots;
+    bslots &= ~1;
+    if (bslots < 2) return 1;
+    m.band_slots = bslots;
+    const int end = m.band_off + bslots * a->band_slot_bytes;
+    if (end > max_end) max_end = end;
+  }
+  a->bar_off = max_end;
   int cols = 32;
-  while (cols < 2 * a->acc_cols) cols *= 2;
+  const int need_cols = a->m[0].tmem_a ? a->a_base + a->m[0].a_slots * a->aslot_cols : 2 * a->acc_cols;
+  while (cols < need_cols) cols *= 2;
   a->tmem_cols = cols;
   const char* dbg = getenv("PMT_TC_DEBUG");
   a->debug = dbg ? atoi(dbg) : 0;
@@ -403,6 +533,8 @@ bool corr1d_bwd_tc_ok(const void* in1, const void* in2, int C, int H, int W, int
   TcBwdArgs a;
   return fill_args(&a, C, H, W, P, passes) == 0;
 }
+
+long long* g_bwd_prof = nullptr;  // device buffer for PMT_BWD_PROFILE builds (set through pmt_debug_set_ptr)
 
 int launch_corr1d_bwd_tc(const float* in1, const float* in2, const float* gout, float* gin1, float* gin2, int B,
                          int C, int H, int W, int P, int passes, cudaStream_t st) {
@@ -423,10 +555,10 @@ int launch_corr1d_bwd_tc(const float* in1, const float* in2, const float* gout, 
   const int64_t gx = tiles < per_mode ? tiles : per_mode;
   if (passes == 3) {
     PMT_CUDA_OK(cudaFuncSetAttribute(corr1d_bwd_tc_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
-    corr1d_bwd_tc_kernel<3><<<dim3((unsigned)gx, 2), BwdCfg<3>::kThreads, smem_bytes, st>>>(tm1, tm2, tmG0, tmG1, gin1, gin2, a);
+    corr1d_bwd_tc_kernel<3><<<dim3((unsigned)gx, 2), BwdCfg<3>::kThreads, smem_bytes, st>>>(tm1, tm2, tmG0, tmG1, gin1, gin2, a, g_bwd_prof);
   } else {
     PMT_CUDA_OK(cudaFuncSetAttribute(corr1d_bwd_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
-    corr1d_bwd_tc_kernel<1><<<dim3((unsigned)gx, 2), BwdCfg<1>::kThreads, smem_bytes, st>>>(tm1, tm2, tmG0, tmG1, gin1, gin2, a);
+    corr1d_bwd_tc_kernel<1><<<dim3((unsigned)gx, 2), BwdCfg<1>::kThreads, smem_bytes, st>>>(tm1, tm2, tmG0, tmG1, gin1, gin2, a, g_bwd_prof);
   }
   PMT_LAUNCH_OK("corr1d_bwd_tc_kernel");
   return PMT_OK;
