@@ -98,14 +98,13 @@ corr1d_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmL, const __grid_const
       tma_prefetch_desc(&tmR);
     }
     const uint32_t bytes = (uint32_t)nboxes * kBoxBytes;
-    int g = 0;
+    int st = 0;
+    uint32_t eph = 1;  // parity to wait for on empty[st] (the first pass over the ring is free)
     for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x) {
       const int wt = tile % a.n_wtiles, h = (tile / a.n_wtiles) % a.H, n = tile / (a.n_wtiles * a.H);
       const int w0 = wt * kTM;
-      for (int k = 0; k < a.n_cchunks; ++k, ++g) {
-        const int st = g % a.stages;
-        const uint32_t ph = (uint32_t)(g / a.stages) & 1u;
-        mbar_wait(&empty[st], ph ^ 1u);
+      for (int k = 0; k < a.n_cchunks; ++k) {
+        mbar_wait(&empty[st], eph);
         unsigned char* sbase = smem + (size_t)st * a.stage_bytes;
         if (lane == 0) mbar_arrive_expect_tx(&full[st], bytes);
         __syncwarp();
@@ -116,56 +115,59 @@ corr1d_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmL, const __grid_const
             tma_load_4d(sbase + lane * kBoxBytes, &tmR, w0 - a.rW - a.delta + 32 * (lane - kLBlocks), h, k * kCK, n,
                         &full[st]);
         }
+        if (++st == a.stages) st = 0, eph ^= 1u;
       }
     }
   } else if (wid == 1) {
     // ===== MMA issuer (one elected lane) =====
+    // Single-thread instruction count is on the critical path: ring positions are running counters and descriptors
+    // are advanced by adding byte offsets (>>4) to the low word of a base descriptor.
     if (lane == 0) {
       const uint32_t idesc1 = tc::make_idesc(2, 1, 1, kTM, a.N1);
       const uint32_t idesc2 = tc::make_idesc(2, 1, 1, kTM, a.N2 > 0 ? a.N2 : 16);
-      const int nb1 = a.N1 / 32;
-      int g = 0, it = 0;
+      const uint64_t d0 = mn_desc(smem_u32(smem), kBoxBytes, 1024);                       // raw ring (hi operand)
+      const uint64_t dl0 = mn_desc(smem_u32(smem + a.lo_ring_off), kBoxBytes, 1024);      // lo ring
+      const uint32_t st_step = (uint32_t)a.stage_bytes >> 4;
+      const uint32_t offB1 = (uint32_t)(kLBlocks * kBoxBytes) >> 4;
+      const uint32_t offB2 = offB1 + ((uint32_t)((a.N1 / 32) * kBoxBytes) >> 4);
+      const bool skip = (a.debug & 16) != 0, two = a.N2 > 0;
+      int st = 0, ls = 0, it = 0;
+      uint32_t fph = 0, lph = 0;
       for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x, ++it) {
         mbar_wait(tmem_empty, ((uint32_t)it & 1u) ^ 1u);  // epilogue of the previous tile has drained TMEM
         tc::fence_after_sync();
-        for (int k = 0; k < a.n_cchunks; ++k, ++g) {
-          const int st = g % a.stages;
-          const uint32_t ph = (uint32_t)(g / a.stages) & 1u;
-          const int ls = g % a.lo_stages;
-          if (kPasses == 3) mbar_wait(&xf_done[ls], (uint32_t)(g / a.lo_stages) & 1u);
-          else mbar_wait(&full[st], ph);
+        for (int k = 0; k < a.n_cchunks; ++k) {
+          if (kPasses == 3) mbar_wait(&xf_done[ls], lph);
+          else mbar_wait(&full[st], fph);
           tc::fence_after_sync();
-          const uint32_t sbase = smem_u32(smem + (size_t)st * a.stage_bytes);
-          const uint32_t lo_delta = smem_u32(smem + a.lo_ring_off + (size_t)ls * a.stage_bytes) - sbase;
+          const uint64_t dh = d0 + (uint64_t)(st_step * (uint32_t)st);
+          const uint64_t dl = dl0 + (uint64_t)(st_step * (uint32_t)ls);
 #pragma unroll
-          for (int kk = 0; kk < kCK / 8 && !(a.debug & 16); ++kk) {
+          for (int kk = 0; kk < kCK / 8; ++kk) {
+            if (skip) break;
             const uint32_t acc = (k > 0 || kk > 0) ? 1u : 0u;
-            const uint32_t a_hi = sbase + kk * 1024;
-            const uint32_t b1_hi = sbase + kLBlocks * kBoxBytes + kk * 1024;
-            const uint32_t b2_hi = b1_hi + nb1 * kBoxBytes;
-            const uint64_t dA = mn_desc(a_hi, kBoxBytes, 1024);
-            const uint64_t dB1 = mn_desc(b1_hi, kBoxBytes, 1024);
-            const uint64_t dB2 = mn_desc(b2_hi, kBoxBytes, 1024);
+            const uint32_t ko = (uint32_t)(kk * 1024) >> 4;
+            const uint64_t dA = dh + ko, dB1 = dh + offB1 + ko, dB2 = dh + offB2 + ko;
             if (kPasses == 3) {
-              const uint64_t dAl = mn_desc(a_hi + lo_delta, kBoxBytes, 1024);
-              const uint64_t dB1l = mn_desc(b1_hi + lo_delta, kBoxBytes, 1024);
-              const uint64_t dB2l = mn_desc(b2_hi + lo_delta, kBoxBytes, 1024);
+              const uint64_t dAl = dl + ko, dB1l = dl + offB1 + ko, dB2l = dl + offB2 + ko;
               // small cross terms first, then the dominant hi*hi term
               tc::mma_tf32(tmem_base, dAl, dB1, idesc1, acc);
               tc::mma_tf32(tmem_base, dA, dB1l, idesc1, 1u);
               tc::mma_tf32(tmem_base, dA, dB1, idesc1, 1u);
-              if (a.N2 > 0) {
+              if (two) {
                 tc::mma_tf32(tmem_base + a.N1, dAl, dB2, idesc2, acc);
                 tc::mma_tf32(tmem_base + a.N1, dA, dB2l, idesc2, 1u);
                 tc::mma_tf32(tmem_base + a.N1, dA, dB2, idesc2, 1u);
               }
             } else {
               tc::mma_tf32(tmem_base, dA, dB1, idesc1, acc);
-              if (a.N2 > 0) tc::mma_tf32(tmem_base + a.N1, dA, dB2, idesc2, acc);
+              if (two) tc::mma_tf32(tmem_base + a.N1, dA, dB2, idesc2, acc);
             }
           }
           tc::mma_commit(&empty[st]);  // ring slot reusable once these MMAs have read it
           if (kPasses == 3) tc::mma_commit(&lo_empty[ls]);
+          if (++st == a.stages) st = 0, fph ^= 1u;
+          if (++ls == a.lo_stages) ls = 0, lph ^= 1u;
         }
         tc::mma_commit(tmem_full);     // accumulator of this tile complete
       }
@@ -216,14 +218,12 @@ corr1d_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmL, const __grid_const
     // ===== transform warps (kPasses == 3): split staged fp32 into tf32 hi + lo =====
     const int t = tid - 6 * 32;  // 0..127
     const int nchunks = nboxes * (kBoxBytes / 16);
-    int g = 0;
+    int st = 0, ls = 0;
+    uint32_t fph = 0, leph = 1;
     for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x) {
-      for (int k = 0; k < a.n_cchunks; ++k, ++g) {
-        const int st = g % a.stages;
-        const uint32_t ph = (uint32_t)(g / a.stages) & 1u;
-        const int ls = g % a.lo_stages;
-        mbar_wait(&full[st], ph);
-        mbar_wait(&lo_empty[ls], ((uint32_t)(g / a.lo_stages) & 1u) ^ 1u);
+      for (int k = 0; k < a.n_cchunks; ++k) {
+        mbar_wait(&full[st], fph);
+        mbar_wait(&lo_empty[ls], leph);
         const unsigned char* sbase = smem + (size_t)st * a.stage_bytes;
         unsigned char* lbase = smem + a.lo_ring_off + (size_t)ls * a.stage_bytes;
         // hi operand = the raw fp32 left in place (kind::tf32 ignores the low 13 mantissa bits, verified on B200:
@@ -241,6 +241,8 @@ corr1d_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmL, const __grid_const
         fence_proxy_async();  // make the rewritten stage visible to the tensor core's async-proxy reads
         __syncwarp();
         if (lane == 0) mbar_arrive(&xf_done[ls]);
+        if (++st == a.stages) st = 0, fph ^= 1u;
+        if (++ls == a.lo_stages) ls = 0, leph ^= 1u;
       }
     }
   }
