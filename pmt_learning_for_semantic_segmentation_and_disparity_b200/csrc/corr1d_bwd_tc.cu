@@ -1,5 +1,5 @@
 // corr1d_bwd_tc.cu -- tensor-core (tcgen05 + TMEM) backward of the 1 x P horizontal correlation.
-// Both gradients are deterministic gathers (no atomics), one launch, blockIdx.y selects the gradient:
+// Both gradients are deterministic gathers (no atomics), one launch; CTAs [0, n_cta0) compute gin1, the rest gin2:
 //   mode 0: gin1[c,x] = sum_j Gd[x][j] * in2[c][x0+oo+j]        mode 1: gin2[c,x] = sum_j Gd[x][j] * in1[c][x0+oo+j]
 // where Gd[x][j] is the band matrix made of g (mode 0: g[j-delta-x][x]; mode 1: g[x+P-1+delta-j][x0+oo+j]).
 // A tile = 128 output columns x of one image row, all C channels (C <= 128):
@@ -59,6 +59,7 @@ struct TcBwdArgs {
   int Cbox;            // channels rounded up to 32 (UMMA N, TMEM columns per accumulator)
   int NKC;             // K chunks per tile
   int n_xtiles, n_tiles;
+  int n_cta0;          // CTAs [0, n_cta0) compute gin1 (mode 0), the rest gin2 (mode 1)
   int n_gboxes;        // mode 0: 32-row boxes of the resident g slice (= raw ring slots)
   int a_base, aslot_cols;  // TMEM A ring: first column, columns per slot (32 hi [+ 32 lo])
   int gd_slot_bytes, gd_lo_off;       // Gd ring slot: hi [16 KB] (+ lo [16 KB])
@@ -97,7 +98,9 @@ struct TileCoord {
   int x0, h, n;
 };
 __device__ __forceinline__ TileCoord tile_coord(const TcBwdArgs& a, int i) {
-  const int t = blockIdx.x + i * gridDim.x;
+  // CTAs of one mode walk that mode's tiles with a stride equal to the number of CTAs of the mode
+  const bool m0 = (int)blockIdx.x < a.n_cta0;
+  const int t = (m0 ? (int)blockIdx.x : (int)blockIdx.x - a.n_cta0) + i * (m0 ? a.n_cta0 : (int)gridDim.x - a.n_cta0);
   TileCoord c;
   c.x0 = (t % a.n_xtiles) * kTM;
   c.h = (t / a.n_xtiles) % a.H;
@@ -125,7 +128,9 @@ corr1d_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmIn1, const __grid_con
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
   unsigned char* gd_ring = smem + a.gd_off;
 
-  const int mode = blockIdx.y;
+  const int mode = (int)blockIdx.x < a.n_cta0 ? 0 : 1;
+  const int cta_in_mode = mode == 0 ? (int)blockIdx.x : (int)blockIdx.x - a.n_cta0;
+  const int ctas_of_mode = mode == 0 ? a.n_cta0 : (int)gridDim.x - a.n_cta0;
   const TcBwdMode m = a.m[mode];
   unsigned char* band_ring = smem + m.band_off;
   const CUtensorMap* tmBand = mode == 0 ? &tmIn2 : &tmIn1;
@@ -137,7 +142,7 @@ corr1d_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmIn1, const __grid_con
   const long long t_start = clock64();
 #endif
   const int band_bytes = a.Cbox * 128;
-  const int n_my = (a.n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;  // tiles of this CTA
+  const int n_my = (a.n_tiles - cta_in_mode + ctas_of_mode - 1) / ctas_of_mode;  // tiles of this CTA
   const int G = n_my * a.NKC;                                                            // chunks of this CTA
 
   if (tid == 0) {
@@ -151,7 +156,7 @@ corr1d_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmIn1, const __grid_con
     }
     for (int s = 0; s < 8; ++s) {
       mbar_init(&raw_full[s], 1);
-      mbar_init(&raw_empty[s], blockIdx.y == 0 ? kBuilders : kGroupWarps);
+      mbar_init(&raw_empty[s], mode == 0 ? kBuilders : kGroupWarps);
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tmem_full[s], 1);
@@ -446,8 +451,8 @@ corr1d_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmIn1, const __grid_con
   }
 
 #ifdef PMT_BWD_PROFILE
-  if (prof != nullptr && blockIdx.x == 0 && lane == 0) {
-    long long* o = prof + ((size_t)blockIdx.y * 32 + wid) * 5;
+  if (prof != nullptr && cta_in_mode == 0 && lane == 0) {
+    long long* o = prof + ((size_t)mode * 32 + wid) * 5;
     o[0] = wait_cyc[0], o[1] = wait_cyc[1], o[2] = wait_cyc[2], o[3] = wait_cyc[3];
     o[4] = clock64() - t_start;
   }
@@ -550,15 +555,23 @@ int launch_corr1d_bwd_tc(const float* in1, const float* in2, const float* gout, 
   const int64_t tiles = (int64_t)B * H * a.n_xtiles;
   PMT_CHECK_ARG(tiles < (1ll << 31), "corr1d tc bwd: too many tiles");
   a.n_tiles = (int)tiles;
-  int per_mode = sm_count() / 2;  // persistent: one CTA per SM, half of the SMs per gradient
-  if (per_mode < 1) per_mode = 1;
-  const int64_t gx = tiles < per_mode ? tiles : per_mode;
+  // persistent: one CTA per SM.  The two gradients cost differently per tile (gin1 builds its A operand in TMEM and
+  // is cheaper), so the SMs are split unevenly to finish together.
+  const int sms = sm_count();
+  int64_t n_cta = 2 * tiles < sms ? 2 * tiles : sms;
+  if (n_cta < 2) n_cta = 2;
+  // measured optimum at the headline shape: 68 of 148 CTAs (3xTF32), 64 of 148 (plain TF32)
+  int n0 = (int)(n_cta * (a.m[0].tmem_a ? (passes == 3 ? 0.46 : 0.432) : 0.5) + 0.5);
+  if (const char* e = getenv("PMT_BWD_SPLIT")) n0 = atoi(e);  // tuning knob
+  if (n0 < 1) n0 = 1;
+  if (n0 > n_cta - 1) n0 = (int)n_cta - 1;
+  a.n_cta0 = n0;
   if (passes == 3) {
     PMT_CUDA_OK(cudaFuncSetAttribute(corr1d_bwd_tc_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
-    corr1d_bwd_tc_kernel<3><<<dim3((unsigned)gx, 2), BwdCfg<3>::kThreads, smem_bytes, st>>>(tm1, tm2, tmG0, tmG1, gin1, gin2, a, g_bwd_prof);
+    corr1d_bwd_tc_kernel<3><<<dim3((unsigned)n_cta), BwdCfg<3>::kThreads, smem_bytes, st>>>(tm1, tm2, tmG0, tmG1, gin1, gin2, a, g_bwd_prof);
   } else {
     PMT_CUDA_OK(cudaFuncSetAttribute(corr1d_bwd_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
-    corr1d_bwd_tc_kernel<1><<<dim3((unsigned)gx, 2), BwdCfg<1>::kThreads, smem_bytes, st>>>(tm1, tm2, tmG0, tmG1, gin1, gin2, a, g_bwd_prof);
+    corr1d_bwd_tc_kernel<1><<<dim3((unsigned)n_cta), BwdCfg<1>::kThreads, smem_bytes, st>>>(tm1, tm2, tmG0, tmG1, gin1, gin2, a, g_bwd_prof);
   }
   PMT_LAUNCH_OK("corr1d_bwd_tc_kernel");
   return PMT_OK;
