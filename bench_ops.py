@@ -122,6 +122,18 @@ def main():
     ramp = torch.arange(D, device=dev, dtype=torch.float32).view(1, D, 1, 1)
     ms = timed(lambda i: torch.sum(torch.softmax(c[i], dim=1) * ramp.repeat(B, 1, H, W), 1), 2)
     report("softargmin_fwd[ATen sequence of the reference]", "config3", ms, cb + 2 * ob, B)
+    # f1: trilinear x4 upsample fused into the soft-argmin vs the reference sequence (upsample -> softmax -> regression)
+    low = [3.0 * torch.randn(B, 1, D // 4, H // 4, W // 4, device=dev) for _ in range(2)]
+    lb = 4 * B * (D // 4) * (H // 4) * (W // 4)
+    ms = timed(lambda i: lib.pmt_upsample_softargmin_fwd_f32(vp(low[i]), vp(out), None, B, D // 4, H // 4, W // 4, D, H, W, sp), 2)
+    report("upsample_softargmin_fwd (fused f1)", "config3 logits (4,1,48,64,128) -> pred (4,256,512)", ms, lb + ob, B)
+
+    def unfused(i):
+        up = torch.nn.functional.interpolate(low[i], size=[D, H, W], mode="trilinear", align_corners=False)[:, 0]
+        return torch.sum(torch.softmax(up, dim=1) * ramp.repeat(B, 1, H, W), 1)
+
+    ms = timed(unfused, 2)
+    report("upsample+softmax+regression [ATen sequence of the reference]", "config3", ms, lb + ob, B)
     del c, gc
 
     # ---- warp (config 4: 540x960, C=3; production 256x512 C=2) --------------------------------------

@@ -108,6 +108,14 @@ int pmt_softargmin_fwd_f32(const float* cost, float* out, float* lse, int B, int
 int pmt_softargmin_bwd_f32(const float* cost, const float* out, const float* lse, const float* gout,
                            float* gcost, int B, int D, int H, int W, void* stream);
 
+/* f1 (next row): F.upsample(cost3, [D,H,W], mode='trilinear') fused into the soft-argmin --
+ * models_psmnet/stackhourglass.py:149-155 (and :138-147 for pred1/pred2).  `lowres` is (B,Dq,Hq,Wq) (the squeezed
+ * (B,1,Dq,Hq,Wq) logits); the (B,D,H,W) upsampled volume is never materialised.  align_corners=False semantics of
+ * ATen (scale = in/out, src = scale*(dst+0.5)-0.5 clamped at 0).  `lse` (B,H,W) may be NULL.  Forward only: the
+ * training path materialises the volume and uses pmt_softargmin_bwd_f32. */
+int pmt_upsample_softargmin_fwd_f32(const float* lowres, float* out, float* lse, int B, int Dq, int Hq,
+                                    int Wq, int D, int H, int W, void* stream);
+
 /* ---------------------------------------------------------------------------------------------
  * a4. apply_disparity(input_images, x_offset, wrap_mode='edge') -- models/torch_dsnet.py:10-86.
  *   x = clamp(w + off[n,0,h,w], 0, W-1); x0 = floor(x); x1 = min(x0+1, W-1)

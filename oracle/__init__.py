@@ -170,3 +170,14 @@ def warp_bwd(img, off, gout):
     goff = np.empty((N, 1, H, W), dtype=np.float32)
     lib().pmt_oracle_warp_bwd(_p(img), _p(off), _p(gout), _p(gimg), _p(goff), N, C, H, W)
     return gimg, goff
+
+
+def upsample_softargmin_fwd(lowres, maxdisp, size):
+    lowres = _c(lowres)
+    if lowres.ndim == 5:
+        lowres = np.ascontiguousarray(lowres[:, 0])
+    B, Dq, Hq, Wq = lowres.shape
+    H, W = int(size[0]), int(size[1])
+    out = np.empty((B, H, W), dtype=np.float32)
+    lib().pmt_oracle_upsample_softargmin_fwd(_p(lowres), _p(out), B, Dq, Hq, Wq, int(maxdisp), H, W)
+    return out

@@ -142,6 +142,17 @@ def main():
                      f"{name}_g1": g1.numpy(), f"{name}_g2": g2.numpy(),
                      f"{name}_patch": np.array(patch), f"{name}_dil": np.array(dil)})
     np.savez(os.path.join(OUT, "corr_small_unpinned.npz"), **blob)
+    # ---- f1 upsample + soft-argmin: the reference's own call sequence (stackhourglass.py:149-155) ----------------
+    import torch.nn.functional as F
+    maxdisp, H, W = 24, 12, 20
+    cost3 = (3.0 * torch.randn(2, 1, maxdisp // 4, H // 4, W // 4, generator=g)).requires_grad_(True)
+    up = F.upsample(cost3, [maxdisp, H, W], mode='trilinear')
+    up = torch.squeeze(up, 1)
+    pred = disparityregression(maxdisp)(F.softmax(up, dim=1))
+    gp = torch.randn(pred.shape, generator=g)
+    (gc3,) = torch.autograd.grad(pred, cost3, gp)
+    np.savez(os.path.join(OUT, "upsoftargmin_small.npz"), cost3=cost3.detach().numpy(), pred=pred.detach().numpy(),
+             gpred=gp.numpy(), gcost3=gc3.numpy(), maxdisp=np.array(maxdisp), size=np.array([H, W]))
     print("wrote", sorted(os.listdir(OUT)))
 
 

@@ -286,6 +286,55 @@ void pmt_oracle_softargmin_bwd(const float* cost, const float* gout, float* gcos
   }
 }
 
+/* f1. F.upsample(cost3, [D,H,W], mode='trilinear') -> squeeze -> softmax(dim=1) -> disparityregression,
+ * models_psmnet/stackhourglass.py:149-155.  ATen's align_corners=False rule: scale = in/out (float),
+ * src = scale*(dst+0.5)-0.5 clamped at 0, i0=(int)src, i1=i0+(i0<in-1), l1=src-i0, l0=1-l1, and the trilinear blend
+ * t0*(h0*(w0*v000+w1*v001)+h1*(w0*v010+w1*v011)) + t1*(...).  Pinned by tests/golden/upsoftargmin_small.npz. */
+static void up_src(float scale, int dst, int in, int* i0, int* i1, float* l0, float* l1) {
+  float src = scale * ((float)dst + 0.5f) - 0.5f;
+  if (src < 0.0f) src = 0.0f;
+  *i0 = (int)src;
+  if (*i0 > in - 1) *i0 = in - 1;
+  *i1 = *i0 + ((*i0 < in - 1) ? 1 : 0);
+  *l1 = src - (float)*i0;
+  *l0 = 1.0f - *l1;
+}
+
+void pmt_oracle_upsample_softargmin_fwd(const float* low, float* out, int B, int Dq, int Hq, int Wq, int D, int H,
+                                        int W) {
+  const float sd = (float)Dq / (float)D, sh = (float)Hq / (float)H, sw = (float)Wq / (float)W;
+  const int64_t qplane = (int64_t)Hq * Wq;
+#pragma omp parallel for schedule(static)
+  for (int64_t q = 0; q < (int64_t)B * H * W; ++q) {
+    const int w = (int)(q % W), h = (int)((q / W) % H), b = (int)(q / ((int64_t)W * H));
+    int h0, h1, w0, w1;
+    float hl0, hl1, wl0, wl1;
+    up_src(sh, h, Hq, &h0, &h1, &hl0, &hl1);
+    up_src(sw, w, Wq, &w0, &w1, &wl0, &wl1);
+    const float* base = low + (int64_t)b * Dq * qplane;
+    float* c = (float*)malloc(sizeof(float) * (size_t)D);
+    float m = -INFINITY;
+    for (int d = 0; d < D; ++d) {
+      int t0, t1;
+      float tl0, tl1;
+      up_src(sd, d, Dq, &t0, &t1, &tl0, &tl1);
+      const float* p0 = base + (int64_t)t0 * qplane;
+      const float* p1 = base + (int64_t)t1 * qplane;
+      const float a0 = hl0 * (wl0 * p0[h0 * Wq + w0] + wl1 * p0[h0 * Wq + w1]) +
+                       hl1 * (wl0 * p0[h1 * Wq + w0] + wl1 * p0[h1 * Wq + w1]);
+      const float a1 = hl0 * (wl0 * p1[h0 * Wq + w0] + wl1 * p1[h0 * Wq + w1]) +
+                       hl1 * (wl0 * p1[h1 * Wq + w0] + wl1 * p1[h1 * Wq + w1]);
+      c[d] = tl0 * a0 + tl1 * a1;
+      m = fmaxf(m, c[d]);
+    }
+    float ssum = 0.0f, acc = 0.0f;
+    for (int d = 0; d < D; ++d) ssum += expf(c[d] - m);
+    for (int d = 0; d < D; ++d) acc += (expf(c[d] - m) / ssum) * (float)d;
+    out[q] = acc;
+    free(c);
+  }
+}
+
 /* ------------------------------------------------------------------------------------------
  * a4. apply_disparity(img, x_offset, wrap_mode='edge') -- models/torch_dsnet.py:10-86.
  * Every arithmetic step is kept in fp32 exactly as the reference does it, INCLUDING the flat

@@ -7,7 +7,8 @@ include/pmt_ops.h.  There is no CPU, PyTorch-eager or Triton fallback: if the li
 from ._lib import PmtOpsError, load as load_library  # noqa: F401
 from .correlation import (SpatialCorrelationSampler, SpatialCorrelationSamplerFunction,  # noqa: F401
                           get_correlation_engine, set_correlation_engine, spatial_correlation_sample)
-from .psmnet import build_concat_volume, disparityregression, matchshifted, softargmin  # noqa: F401
+from .psmnet import (build_concat_volume, disparityregression, matchshifted, softargmin,  # noqa: F401
+                     upsample_softargmin)
 from .warp import apply_disparity  # noqa: F401
 from .compat import install_reference_shims  # noqa: F401
 

@@ -34,6 +34,7 @@ _SIGNATURES = {
     "pmt_dispreg_bwd_f32": [_P, _P, _I, _I, _I, _I, _P],
     "pmt_softargmin_fwd_f32": [_P, _P, _P, _I, _I, _I, _I, _P],
     "pmt_softargmin_bwd_f32": [_P, _P, _P, _P, _P, _I, _I, _I, _I, _P],
+    "pmt_upsample_softargmin_fwd_f32": [_P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P],
     "pmt_warp1d_fwd_f32": [_P, _P, _P, _I, _I, _I, _I, _I, _P],
     "pmt_warp1d_bwd_f32": [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P],
     "pmt_corr1d_fwd_bwd_host_f32": [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I],

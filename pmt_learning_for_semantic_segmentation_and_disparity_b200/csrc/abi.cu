@@ -31,6 +31,7 @@ int launch_softargmin_fwd(const float*, float*, float*, int, int, int, int, cuda
 int launch_softargmin_bwd(const float*, const float*, const float*, const float*, float*, int, int,
                           int, int, cudaStream_t);
 int launch_dispreg_fwd(const float*, float*, int, int, int, int, cudaStream_t);
+int launch_upsample_softargmin_fwd(const float*, float*, float*, int, int, int, int, int, int, int, cudaStream_t);
 int launch_dispreg_bwd(const float*, float*, int, int, int, int, cudaStream_t);
 int launch_warp_fwd(const float*, const float*, float*, int, int, int, int, int, cudaStream_t);
 int launch_warp_bwd(const float*, const float*, const float*, float*, float*, int, int, int, int, int,
@@ -299,6 +300,13 @@ int pmt_softargmin_bwd_f32(const float* cost, const float* out, const float* lse
   PMT_CHECK_ARG(cost && out && lse && gout && gcost, "softargmin backward: null pointer");
   PMT_CHECK_ARG(B >= 0 && D >= 1 && H >= 0 && W >= 0, "softargmin: bad dimension");
   return launch_softargmin_bwd(cost, out, lse, gout, gcost, B, D, H, W, static_cast<cudaStream_t>(stream));
+}
+
+int pmt_upsample_softargmin_fwd_f32(const float* lowres, float* out, float* lse, int B, int Dq, int Hq, int Wq, int D,
+                                    int H, int W, void* stream) {
+  PMT_CHECK_ARG(lowres && out, "upsample_softargmin: null pointer");
+  PMT_CHECK_ARG(B >= 0 && Dq >= 1 && Hq >= 1 && Wq >= 1 && D >= 1 && H >= 0 && W >= 0, "upsample_softargmin: bad dimension");
+  return launch_upsample_softargmin_fwd(lowres, out, lse, B, Dq, Hq, Wq, D, H, W, static_cast<cudaStream_t>(stream));
 }
 
 int pmt_warp1d_fwd_f32(const float* img, const float* off, float* out, int N, int C, int H, int W,

@@ -123,3 +123,48 @@ def softargmin(cost: torch.Tensor) -> torch.Tensor:
     if cost.dim() != 4 or cost.size(1) < 1:
         raise ValueError(f"expected (B,D,H,W) with D>=1, got {tuple(cost.shape)}")
     return _SoftArgmin.apply(cost)
+
+
+class _UpsampleSoftArgmin(Function):
+    """Forward: fused kernel (the (B,D,H,W) volume is never written).  Backward: the training path needs the
+    upsampled logits anyway (g_cost = g * p_d * (d - out)), so it re-materialises them with ATen's trilinear
+    upsample, runs the soft-argmin backward kernel and lets autograd transpose the interpolation."""
+
+    @staticmethod
+    def forward(ctx, cost_lowres, maxdisp, height, width):
+        c = U.require_cuda_f32(cost_lowres, "cost")
+        if c.dim() == 5:
+            if c.size(1) != 1:
+                raise ValueError(f"expected (B,1,Dq,Hq,Wq), got {tuple(c.shape)}")
+            c4 = c[:, 0]
+        elif c.dim() == 4:
+            c4 = c
+        else:
+            raise ValueError(f"expected (B,1,Dq,Hq,Wq) or (B,Dq,Hq,Wq), got {tuple(c.shape)}")
+        c4 = c4.contiguous()
+        B, Dq, Hq, Wq = c4.shape
+        D, H, W = int(maxdisp), int(height), int(width)
+        out = torch.empty((B, H, W), device=c.device, dtype=torch.float32)
+        U.call("pmt_upsample_softargmin_fwd_f32", c.device, U.ptr(c4), U.ptr(out), U.ptr(None), B, Dq, Hq, Wq, D, H, W)
+        ctx.save_for_backward(cost_lowres)
+        ctx.size = (D, H, W)
+        return out
+
+    @staticmethod
+    def backward(ctx, gout):
+        (cost_lowres,) = ctx.saved_tensors
+        D, H, W = ctx.size
+        with torch.enable_grad():
+            c = cost_lowres.detach().requires_grad_(True)
+            c5 = c if c.dim() == 5 else c.unsqueeze(1)
+            up = torch.nn.functional.interpolate(c5, size=[D, H, W], mode="trilinear", align_corners=False)[:, 0]
+            out = softargmin(up)
+        (g,) = torch.autograd.grad(out, c, gout)
+        return g, None, None, None
+
+
+def upsample_softargmin(cost_lowres: torch.Tensor, maxdisp: int, size) -> torch.Tensor:
+    """pred = disparityregression(maxdisp)(softmax(squeeze(F.upsample(cost, [maxdisp, H, W], mode='trilinear'), 1), 1))
+    -- models_psmnet/stackhourglass.py:149-155 -- in one kernel.  `size` = (H, W) of the full-resolution image."""
+    H, W = int(size[0]), int(size[1])
+    return _UpsampleSoftArgmin.apply(cost_lowres, int(maxdisp), H, W)

@@ -123,3 +123,30 @@ def test_softargmin_properties_full_batch(pmt):
     idx = torch.randint(0, D, (1, 1, 4, 8), device=DEV)
     onehot.scatter_(1, idx, 40.0)
     assert torch.allclose(pmt.softargmin(onehot), idx[:, 0].float(), atol=1e-4)
+
+
+# ---- f1: F.upsample(trilinear) + softmax + disparityregression in one kernel ---------------------------------
+def test_upsample_softargmin_golden(pmt, golden_dir):
+    d = np.load(os.path.join(golden_dir, "upsoftargmin_small.npz"))
+    c = torch.from_numpy(d["cost3"]).to(DEV).requires_grad_(True)
+    pred = pmt.upsample_softargmin(c, int(d["maxdisp"]), tuple(int(v) for v in d["size"]))
+    assert rel_err(npy(pred), d["pred"]) <= FP32_TOL
+    pred.backward(torch.from_numpy(d["gpred"]).to(DEV))
+    assert rel_err(npy(c.grad), d["gcost3"]) <= FP32_TOL
+
+
+@pytest.mark.parametrize("B,Dq,Hq,Wq,scale", [(2, 48, 64, 128, 4),      # config 3: (48,64,128) -> (192,256,512)
+                                              (1, 5, 7, 9, 3), (1, 1, 2, 3, 4)])
+def test_upsample_softargmin_vs_oracle_and_unfused(pmt, B, Dq, Hq, Wq, scale):
+    rng = np.random.default_rng(Dq)
+    low = (3.0 * rng.standard_normal((B, 1, Dq, Hq, Wq))).astype(np.float32)
+    D, H, W = Dq * scale, Hq * scale, Wq * scale
+    c = torch.from_numpy(low).to(DEV)
+    pred = pmt.upsample_softargmin(c, D, (H, W))
+    assert pred.shape == (B, H, W)
+    if B * H * W <= 300000:
+        assert rel_err(npy(pred), oracle.upsample_softargmin_fwd(low, D, (H, W))) <= FP32_TOL
+    # the unfused sequence the reference runs (ATen upsample -> softmax -> regression), on the GPU
+    up = torch.nn.functional.interpolate(c, size=[D, H, W], mode="trilinear", align_corners=False)[:, 0]
+    ref = (torch.softmax(up, 1) * torch.arange(D, device=DEV).view(1, D, 1, 1)).sum(1)
+    assert float((pred - ref).abs().max()) / float(ref.abs().max()) <= FP32_TOL

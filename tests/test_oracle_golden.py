@@ -148,3 +148,10 @@ def test_corr_general_kernel_matches_conv_definition():
                     x = ap[0, :, u:u + 3, v:v + 3]
                     y = bp[0, :, u + ph - 1:u + ph - 1 + 3, v + pw - 1:v + pw - 1 + 3]
                     assert abs(float((x * y).sum()) - float(out[0, ph, pw, h, w])) < 1e-4
+
+
+# ---- f1 fused trilinear upsample + soft-argmin: pinned by the reference's own call sequence -------
+def test_upsample_softargmin_oracle_vs_reference(golden_dir):
+    d = load(golden_dir, "upsoftargmin_small.npz")
+    out = oracle.upsample_softargmin_fwd(d["cost3"], int(d["maxdisp"]), d["size"])
+    assert rel_err(out, d["pred"]) <= 1e-5
