@@ -68,7 +68,7 @@ struct TcBwdArgs {
   int tmem_cols;
   int acc_cols;        // TMEM columns per accumulator (Cbox, or 2*Cbox for 3xTF32: hi and lo column blocks)
   TcBwdMode m[2];
-  int debug;           // PMT_TC_DEBUG ablation bits: 4 skip Gd build, 32 skip band split, 16 skip MMA, 8 skip epilogue
+  int debug;           // PMT_TC_DEBUG ablation bits: 4 skip Gd build, 32 skip band split, 16 skip MMA, 8 skip epilogue, 2048 / 4096 skip gin2 / gin1
 };
 
 // K-major, 128-byte swizzle: element (row, col) of a [rows][32 floats] chunk
@@ -90,8 +90,12 @@ __device__ __forceinline__ float lo_tf32(float x) {
     mbar_wait(bar, par);                           \
     wait_cyc[slot] += clock64() - _t0;             \
   } while (0)
+#define PSEC_BEGIN() const long long _s0 = clock64()
+#define PSEC_END(slot) sec_cyc[slot] += clock64() - _s0
 #else
 #define PWAIT(slot, bar, par) mbar_wait(bar, par)
+#define PSEC_BEGIN()
+#define PSEC_END(slot)
 #endif
 
 struct TileCoord {
@@ -139,10 +143,12 @@ corr1d_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmIn1, const __grid_con
   const int tid = threadIdx.x, wid = tid >> 5, lane = tid & 31;
 #ifdef PMT_BWD_PROFILE
   long long wait_cyc[4] = {0, 0, 0, 0};
+  long long sec_cyc[4] = {0, 0, 0, 0};
   const long long t_start = clock64();
 #endif
   const int band_bytes = a.Cbox * 128;
-  const int n_my = (a.n_tiles - cta_in_mode + ctas_of_mode - 1) / ctas_of_mode;  // tiles of this CTA
+  int n_my = (a.n_tiles - cta_in_mode + ctas_of_mode - 1) / ctas_of_mode;  // tiles of this CTA
+  if (a.debug & (mode == 0 ? 4096 : 2048)) n_my = 0;   // ablation: run one gradient only
   const int G = n_my * a.NKC;                                                            // chunks of this CTA
 
   if (tid == 0) {
@@ -246,6 +252,7 @@ corr1d_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmIn1, const __grid_con
           if (kPasses == 1) PWAIT(2, &band_full[bs], bph);
           tc::fence_after_sync();
           const uint64_t dB = dB0 + (uint64_t)(b_step * (uint32_t)bs);
+          { PSEC_BEGIN();
           if (!skip) {
             if (tmem_a) {
               const uint32_t ta = tmem_base + (uint32_t)(a.a_base + gs * a.aslot_cols);
@@ -275,8 +282,11 @@ corr1d_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmIn1, const __grid_con
               }
             }
           }
+          PSEC_END(0); }
+          { PSEC_BEGIN();
           tc::mma_commit(&gd_empty[gs]);
           tc::mma_commit(&band_empty[bs]);
+          PSEC_END(1); }
           if (++gs == m.a_slots) gs = 0, gph ^= 1u;
           if (++bs == m.band_slots) bs = 0, bph ^= 1u;
         }
@@ -351,6 +361,7 @@ corr1d_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmIn1, const __grid_con
           while (boxes_ready < need) { PWAIT(0, &raw_full[boxes_ready], (uint32_t)i & 1u); ++boxes_ready; }
           PWAIT(1, &gd_empty[gs], gph ^ 1u);
           const float* Gt = reinterpret_cast<const float*>(smem);
+          { PSEC_BEGIN();
           if (m.tmem_a) {
             // A operand straight into TMEM: thread = Gd row x (TMEM lane), kCols consecutive band columns per warp
             constexpr int kCols = 32 / (kGroupWarps / 4);
@@ -396,6 +407,7 @@ corr1d_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmIn1, const __grid_con
                     make_float4(lo_tf32(v[0]), lo_tf32(v[1]), lo_tf32(v[2]), lo_tf32(v[3]));
             }
           }
+          PSEC_END(0); }
           // hand back every box this warp will not read again (it visits chunks k, k+2, ...): box b is last used by
           // chunk min(NKC-1, b+koff), so it is dead for this warp once k >= that chunk - 1
           __syncwarp();
@@ -414,35 +426,62 @@ corr1d_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmIn1, const __grid_con
           PWAIT(0, &raw_full[slot], rph);
           PWAIT(1, &gd_empty[gs], gph ^ 1u);
           const float* raw = reinterpret_cast<const float*>(smem + slot * kRawSlot1);
+          { PSEC_BEGIN();
+          if (!(a.debug & 4)) {
+            // 32 warp tasks per chunk (4 Gd rows x 32 columns, lane = column); this warp takes tasks gw, gw+G, ...
+            // All loads are issued before the first store so the LDS latency is paid once per chunk, not per row.
+            constexpr int kTasks = 32 / kGroupWarps;
+            float v[kTasks * 4];
+            // Gd row xl = 4*(gw + G*i) + t reads g[p_first + xl + 31 - lane][column lane]
+            const float* src = raw + (4 * gw + 31 - lane) * kKC + lane;
 #pragma unroll
-          for (int r = gw; r < 32; r += kGroupWarps) {          // 32 warp tasks per chunk: 4 rows x 32 columns (lane = column)
-            if (a.debug & 4) break;
+            for (int i = 0; i < kTasks; ++i)
 #pragma unroll
-            for (int t = 0; t < 4; ++t) {
-              const int xl = 4 * r + t;
-              const float v = raw[(xl + 31 - lane) * kKC + lane];   // g[p_first + xl + 31 - jj][column jj]
-              const uint32_t off = kmajor_off(xl, lane);
-              *reinterpret_cast<float*>(sa + off) = v;
-              if (kPasses == 3) *reinterpret_cast<float*>(sa + a.gd_lo_off + off) = lo_tf32(v);
-            }
+              for (int t = 0; t < 4; ++t) v[4 * i + t] = src[(4 * kGroupWarps * i + t) * kKC];
+            // K-major SW128 offset of (xl, lane): xl & 7 = 4*(gw & 1) + t and xl >> 3 = (gw >> 1) + (G/2)*i
+            unsigned char* dst = sa + (gw >> 1) * 1024 + 4 * (gw & 1) * 128 + ((lane & 3) << 2);
+#pragma unroll
+            for (int i = 0; i < kTasks; ++i)
+#pragma unroll
+              for (int t = 0; t < 4; ++t) {
+                const uint32_t off = (uint32_t)((kGroupWarps / 2) * i * 1024 + t * 128) +
+                                     (uint32_t)((((lane >> 2) ^ (4 * (gw & 1) + t)) & 7) << 4);
+                *reinterpret_cast<float*>(dst + off) = v[4 * i + t];
+                if (kPasses == 3) *reinterpret_cast<float*>(dst + a.gd_lo_off + off) = lo_tf32(v[4 * i + t]);
+              }
           }
+          PSEC_END(0); }
           __syncwarp();
           if (lane == 0) mbar_arrive(&raw_empty[slot]);
         }
         if (kPasses == 3) {
           // split the landed feature band chunk into hi / lo (position-wise, layout agnostic)
           PWAIT(2, &band_full[bs], bph);
+          PSEC_BEGIN();
           unsigned char* sb = band_ring + (size_t)bs * a.band_slot_bytes;
           const int nch = band_bytes / 16;
-          for (int c = (gw * 32 + lane); c < nch && !(a.debug & 32); c += kGroupWarps * 32) {
-            const float4 x = *reinterpret_cast<const float4*>(sb + 16 * c);
-            *reinterpret_cast<float4*>(sb + a.band_lo_off + 16 * c) =
-                make_float4(lo_tf32(x.x), lo_tf32(x.y), lo_tf32(x.z), lo_tf32(x.w));
+          if (!(a.debug & 32)) {
+            constexpr int kStride = kGroupWarps * 32;
+            const int c0 = gw * 32 + lane;
+            for (int cb = c0; cb < nch; cb += 2 * kStride) {   // 2 loads in flight (C=64: one round)
+              float4 x[2];
+#pragma unroll
+              for (int u = 0; u < 2; ++u)
+                if (cb + u * kStride < nch) x[u] = *reinterpret_cast<const float4*>(sb + 16 * (cb + u * kStride));
+#pragma unroll
+              for (int u = 0; u < 2; ++u)
+                if (cb + u * kStride < nch)
+                  *reinterpret_cast<float4*>(sb + a.band_lo_off + 16 * (cb + u * kStride)) =
+                      make_float4(lo_tf32(x[u].x), lo_tf32(x[u].y), lo_tf32(x[u].z), lo_tf32(x[u].w));
+            }
           }
+          PSEC_END(2);
         }
+        { PSEC_BEGIN();
         fence_proxy_async();
         __syncwarp();
         if (lane == 0) mbar_arrive(&gd_built[gs]);
+        PSEC_END(3); }
         advance2(gs, gph, m.a_slots);
         advance2(bs, bph, m.band_slots);
         advance2(rs, rph, kRawSlots1);
@@ -452,9 +491,10 @@ corr1d_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmIn1, const __grid_con
 
 #ifdef PMT_BWD_PROFILE
   if (prof != nullptr && cta_in_mode == 0 && lane == 0) {
-    long long* o = prof + ((size_t)mode * 32 + wid) * 5;
+    long long* o = prof + ((size_t)mode * 32 + wid) * 10;
     o[0] = wait_cyc[0], o[1] = wait_cyc[1], o[2] = wait_cyc[2], o[3] = wait_cyc[3];
     o[4] = clock64() - t_start;
+    o[5] = sec_cyc[0], o[6] = sec_cyc[1], o[7] = sec_cyc[2], o[8] = sec_cyc[3];
   }
 #endif
   tc::fence_before_sync();
@@ -560,8 +600,8 @@ int launch_corr1d_bwd_tc(const float* in1, const float* in2, const float* gout, 
   const int sms = sm_count();
   int64_t n_cta = 2 * tiles < sms ? 2 * tiles : sms;
   if (n_cta < 2) n_cta = 2;
-  // measured optimum at the headline shape: 68 of 148 CTAs (3xTF32), 64 of 148 (plain TF32)
-  int n0 = (int)(n_cta * (a.m[0].tmem_a ? (passes == 3 ? 0.46 : 0.432) : 0.5) + 0.5);
+  // measured optimum at the headline shape: 72 of 148 CTAs (3xTF32), 64 of 148 (plain TF32)
+  int n0 = (int)(n_cta * (a.m[0].tmem_a ? (passes == 3 ? 0.4865 : 0.432) : 0.5) + 0.5);
   if (const char* e = getenv("PMT_BWD_SPLIT")) n0 = atoi(e);  // tuning knob
   if (n0 < 1) n0 = 1;
   if (n0 > n_cta - 1) n0 = (int)n_cta - 1;

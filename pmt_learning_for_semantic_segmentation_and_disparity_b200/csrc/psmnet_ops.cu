@@ -4,6 +4,8 @@
 //   soft-argmin   : F.softmax(dim=1) + disparityregression, stackhourglass.py:142-155
 // All four are HBM-bound streaming kernels: every input element is read once and every output
 // element written once with 128-bit accesses; grids are sized in multiples of the SM count.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace pmt {
@@ -89,6 +91,90 @@ __global__ void __launch_bounds__(256) concat_bwd_kernel(const float* __restrict
         if (w + d0 + i < W) acc += __ldg(g + i * dstride + w + d0 + i);
       gtgt[(((int64_t)b * C + (c2 - C)) * H + h) * (int64_t)W + w] = acc;
     }
+  }
+}
+
+// Vectorised variant (W % 4 == 0, d0 % 4 == 0, 16-byte aligned pointers): one thread per 4 consecutive columns.
+// Reference half: aligned 128-bit loads, per-element mask.  Target half: the 4 needed elements g[i][w+s..w+s+3]
+// (s = d0+i) straddle two aligned vectors unless s % 4 == 0; planes are walked 4 at a time so the in-vector offset
+// is a compile-time constant (7 vector loads per 4 planes; the second vector of a thread is the first vector of its
+// neighbour, so it hits L1).  Planes are still added in descending order, like autograd does.
+__device__ __forceinline__ float4 ldg4_guard(const float* row, int col, int W) {
+  return col < W ? __ldg(reinterpret_cast<const float4*>(row + col)) : make_float4(0.f, 0.f, 0.f, 0.f);
+}
+template <int R>
+__device__ __forceinline__ float4 shift_pick(const float4& a, const float4& b) {   // elements R..R+3 of (a,b)
+  if (R == 0) return a;
+  if (R == 1) return make_float4(a.y, a.z, a.w, b.x);
+  if (R == 2) return make_float4(a.z, a.w, b.x, b.y);
+  return make_float4(a.w, b.x, b.y, b.z);
+}
+
+__global__ void __launch_bounds__(256) concat_bwd_vec_kernel(const float* __restrict__ gcost,
+                                                             float* __restrict__ gref, float* __restrict__ gtgt,
+                                                             int B, int C, int D, int H, int W, int d0,
+                                                             int64_t total4) {
+  const int64_t dstride = (int64_t)H * W;
+  const int W4 = W >> 2;
+  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total4;
+       idx += (int64_t)gridDim.x * blockDim.x) {
+    const int w = (int)(idx % W4) * 4;
+    int64_t t = idx / W4;
+    const int h = (int)(t % H);
+    t /= H;
+    const int c2 = (int)(t % (2 * C));
+    const int b = (int)(t / (2 * C));
+    const bool is_tgt = c2 >= C;
+    const float* g = gcost + ((((int64_t)b * 2 * C + c2) * D) * H + h) * (int64_t)W;
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+    auto add_masked = [&](const float4& v, int s) {   // plane with shift s contributes where the index is in range
+      const float e[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const bool ok = is_tgt ? (w + u + s < W) : (w + u >= s);
+        if (ok) acc[u] += e[u];
+      }
+    };
+    int i = D - 1;
+    for (; (i & 3) != 3; --i) {   // tail planes (D % 4 != 0): generic offsets
+      const int s = d0 + i;
+      const float* row = g + i * dstride;
+      float4 v;
+      if (!is_tgt) {
+        v = ldg4_guard(row, w, W);
+      } else {
+        const int base = (w + s) & ~3, r = (w + s) & 3;
+        const float4 a0 = ldg4_guard(row, base, W), a1 = ldg4_guard(row, base + 4, W);
+        v = r == 0 ? a0 : r == 1 ? shift_pick<1>(a0, a1) : r == 2 ? shift_pick<2>(a0, a1) : shift_pick<3>(a0, a1);
+      }
+      add_masked(v, s);
+    }
+    for (; i >= 3; i -= 4) {      // planes i, i-1, i-2, i-3 with i % 4 == 3
+      const int s0 = d0 + i - 3;  // multiple of 4
+      const float* row = g + (int64_t)(i - 3) * dstride;
+      if (!is_tgt) {
+        float4 v[4];
+#pragma unroll
+        for (int r = 0; r < 4; ++r) v[r] = ldg4_guard(row + r * dstride, w, W);
+#pragma unroll
+        for (int r = 3; r >= 0; --r) add_masked(v[r], s0 + r);
+      } else {
+        const int base = w + s0;
+        float4 a[4], bb[4];
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+          a[r] = ldg4_guard(row + r * dstride, base, W);
+          if (r > 0) bb[r] = ldg4_guard(row + r * dstride, base + 4, W);
+        }
+        add_masked(shift_pick<3>(a[3], bb[3]), s0 + 3);
+        add_masked(shift_pick<2>(a[2], bb[2]), s0 + 2);
+        add_masked(shift_pick<1>(a[1], bb[1]), s0 + 1);
+        add_masked(a[0], s0);
+      }
+    }
+    float* o = (is_tgt ? gtgt + (((int64_t)b * C + (c2 - C)) * H + h) * (int64_t)W
+                       : gref + (((int64_t)b * C + c2) * H + h) * (int64_t)W) + w;
+    *reinterpret_cast<float4*>(o) = make_float4(acc[0], acc[1], acc[2], acc[3]);
   }
 }
 
@@ -284,6 +370,12 @@ __global__ void __launch_bounds__(256) dispreg_bwd_kernel(const float* __restric
 // clamped at 0, scale = in/out), blends consecutive planes along d and feeds the online softmax -- the upsampled
 // volume never touches HBM (reads 1.57 MB instead of 100.7 MB per pair).
 // ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ float fast_exp2(float x) {   // MUFU.EX2; exp2(-inf) = 0
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
 struct UpArgs {
   int B, Dq, Hq, Wq, D, H, W;
   float sd, sh, sw;  // in/out scale per axis
@@ -371,6 +463,92 @@ __global__ void __launch_bounds__(256) upsample_softargmin_fwd_kernel(const floa
   }
 }
 
+// Tiled variant: a CTA owns a kUpTH x kUpTW block of output pixels and stages the low-res footprint of that block
+// (every plane; a few rows x a few columns) in shared memory, so the 4 spatial taps per plane are LDS (mostly
+// broadcast: 4 neighbouring pixels share their taps) instead of scattered global loads.  Same arithmetic, same order.
+constexpr int kUpTH = 4, kUpTW = 64;
+
+__global__ void __launch_bounds__(kUpTH * kUpTW) upsample_softargmin_tiled_kernel(const float* __restrict__ lowres,
+                                                                                   float* __restrict__ out,
+                                                                                   float* __restrict__ lse, UpArgs a,
+                                                                                   int fr_max, int fc_max) {
+  extern __shared__ float up_smem[];
+  int* tab_beg = reinterpret_cast<int*>(up_smem);   // [Dq+1]: first output plane whose lower source plane is >= q
+  float* tab_l1 = up_smem + a.Dq + 1;                // [D]: weight of the upper source plane
+  float* tile = up_smem + a.Dq + 1 + a.D;            // [Dq][fr][fc]
+  const int tid = threadIdx.x;
+  const int h_first = blockIdx.y * kUpTH, w_first = blockIdx.x * kUpTW, b = blockIdx.z;
+  const int h_last = min(h_first + kUpTH, a.H) - 1, w_last = min(w_first + kUpTW, a.W) - 1;
+  int r0, r1, c0, c1, tmp;
+  float f0, f1;
+  src_index(a.sh, h_first, a.Hq, r0, tmp, f0, f1);
+  src_index(a.sh, h_last, a.Hq, tmp, r1, f0, f1);
+  src_index(a.sw, w_first, a.Wq, c0, tmp, f0, f1);
+  src_index(a.sw, w_last, a.Wq, tmp, c1, f0, f1);
+  const int fr = r1 - r0 + 1, fc = c1 - c0 + 1;   // <= fr_max, fc_max (host-side bound)
+  for (int d = tid; d <= a.D; d += blockDim.x) {
+    int i0 = a.Dq, i1 = a.Dq, ip = -1;
+    float l0, l1 = 0.f;
+    if (d < a.D) src_index(a.sd, d, a.Dq, i0, i1, l0, l1);
+    if (d > 0) {
+      int j1;
+      float m0, m1;
+      src_index(a.sd, d - 1, a.Dq, ip, j1, m0, m1);
+    }
+    if (d < a.D) tab_l1[d] = (i1 == i0) ? 0.f : l1;   // at the last plane both taps coincide
+    for (int q = ip + 1; q <= i0 && q <= a.Dq; ++q) tab_beg[q] = d;   // i0 is non-decreasing in d
+  }
+  const int64_t qplane = (int64_t)a.Hq * a.Wq;
+  const float* base = lowres + (int64_t)b * a.Dq * qplane;
+  const int per_plane = fr * fc;
+  for (int i = tid; i < a.Dq * per_plane; i += blockDim.x) {
+    const int q = i / per_plane, rem = i - q * per_plane;
+    const int r = rem / fc, c = rem - r * fc;
+    tile[i] = __ldg(base + q * qplane + (int64_t)(r0 + r) * a.Wq + (c0 + c));
+  }
+  __syncthreads();
+  const int w = w_first + (tid % kUpTW), h = h_first + (tid / kUpTW);
+  if (w >= a.W || h >= a.H) return;
+  int h0, h1, w0, w1;
+  float hl0, hl1, wl0, wl1;
+  src_index(a.sh, h, a.Hq, h0, h1, hl0, hl1);
+  src_index(a.sw, w, a.Wq, w0, w1, wl0, wl1);
+  const float* p00 = tile + (h0 - r0) * fc + (w0 - c0);
+  const int d01 = w1 - w0, d10 = (h1 - h0) * fc;
+  // bilinear sample of low-res plane q at this pixel, pre-multiplied by log2(e) (the soft-max runs in base 2)
+  auto plane = [&](int q) {
+    const float* p = p00 + q * per_plane;
+    return kLog2e * (hl0 * (wl0 * p[0] + wl1 * p[d01]) + hl1 * (wl0 * p[d10] + wl1 * p[d10 + d01]));
+  };
+  // Output planes d in [beg[q], beg[q+1]) blend source planes q and q+1: x_d = s_q + l1_d * (s_{q+1} - s_q), a convex
+  // combination, so max(s_q, s_{q+1}) bounds every x_d of the group: the running maximum is updated once per source
+  // plane (one rescale) instead of once per output plane.
+  float s_cur = plane(0);
+  float m = -INFINITY, s = 0.f, t = 0.f;
+  float df = (float)tab_beg[0];
+  for (int q = 0; q < a.Dq; ++q) {
+    const float s_nxt = plane(q + 1 < a.Dq ? q + 1 : q);
+    const int dend = tab_beg[q + 1];
+    int d = tab_beg[q];
+    if (d < dend) {
+      const float mn = fmaxf(m, fmaxf(s_cur, s_nxt));
+      const float sc = fast_exp2(m - mn);
+      s *= sc, t *= sc, m = mn;
+      const float c = s_cur - mn, diff = s_nxt - s_cur;
+      for (; d < dend; ++d) {
+        const float e = fast_exp2(fmaf(tab_l1[d], diff, c));
+        s += e;
+        t = fmaf(e, df, t);
+        df += 1.f;
+      }
+    }
+    s_cur = s_nxt;
+  }
+  const int64_t idx = ((int64_t)b * a.H + h) * a.W + w;
+  out[idx] = t / s;
+  if (lse != nullptr) lse[idx] = (m + log2f(s)) * kLn2;
+}
+
 int stream_grid(int64_t nthreads) {
   const int64_t blocks = ceil_div64(nthreads, 256);
   const int64_t cap = (int64_t)sm_count() * 8;  // 8 x 256 threads = full residency per SM
@@ -400,6 +578,11 @@ int launch_concat_bwd(const float* gcost, float* gref, float* gtgt, int B, int C
                       int d0, cudaStream_t st) {
   const int64_t total = (int64_t)B * 2 * C * H * W;
   if (total == 0) return PMT_OK;
+  if (W % 4 == 0 && d0 % 4 == 0 && d0 >= 0 && aligned16(gcost) && aligned16(gref) && aligned16(gtgt)) {
+    concat_bwd_vec_kernel<<<stream_grid(total / 4), 256, 0, st>>>(gcost, gref, gtgt, B, C, D, H, W, d0, total / 4);
+    PMT_LAUNCH_OK("concat_bwd_vec_kernel");
+    return PMT_OK;
+  }
   concat_bwd_kernel<<<stream_grid(total), 256, 0, st>>>(gcost, gref, gtgt, B, C, D, H, W, d0, total);
   PMT_LAUNCH_OK("concat_bwd_kernel");
   return PMT_OK;
@@ -442,6 +625,20 @@ int launch_upsample_softargmin_fwd(const float* lowres, float* out, float* lse, 
   if (total == 0) return PMT_OK;
   UpArgs a{B, Dq, Hq, Wq, D, H, W, (float)Dq / (float)D, (float)Hq / (float)H, (float)Wq / (float)W};
   PMT_CHECK_ARG(D <= 4096, "upsample_softargmin: maxdisp %d too large for the weight table", D);
+  // footprint bound of a kUpTH x kUpTW output block: (block-1)*scale + 2 source rows/columns, +1 for rounding
+  const int fr_max = (int)((kUpTH - 1) * a.sh) + 3 < Hq ? (int)((kUpTH - 1) * a.sh) + 3 : Hq;
+  const int fc_max = (int)((kUpTW - 1) * a.sw) + 3 < Wq ? (int)((kUpTW - 1) * a.sw) + 3 : Wq;
+  const size_t tile_bytes = (size_t)(Dq + 1 + D) * 4 + (size_t)Dq * fr_max * fc_max * 4;
+  const int64_t gy = ceil_div64(H, kUpTH), gx = ceil_div64(W, kUpTW);
+  static const bool force_gather = getenv("PMT_UPSOFT_GATHER") != nullptr;
+  if (tile_bytes <= 64 * 1024 && gy <= 65535 && B <= 65535 && !force_gather) {
+    PMT_CUDA_OK(cudaFuncSetAttribute(upsample_softargmin_tiled_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     64 * 1024));
+    upsample_softargmin_tiled_kernel<<<dim3((unsigned)gx, (unsigned)gy, (unsigned)B), kUpTH * kUpTW, tile_bytes, st>>>(
+        lowres, out, lse, a, fr_max, fc_max);
+    PMT_LAUNCH_OK("upsample_softargmin_tiled_kernel");
+    return PMT_OK;
+  }
   upsample_softargmin_fwd_kernel<<<stream_grid(total), 256, (size_t)D * 8, st>>>(lowres, out, lse, a, total);
   PMT_LAUNCH_OK("upsample_softargmin_fwd_kernel");
   return PMT_OK;

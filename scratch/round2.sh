@@ -1,0 +1,13 @@
+#!/bin/bash
+mkdir -p gpurun_out
+{
+timeout 900 python -m pytest tests -x -q -m gpu 2>&1 | tail -4
+timeout 300 python bench_ops.py > gpurun_out/ops.jsonl 2> gpurun_out/ops.err; echo "ops rc=$?"
+python - <<'P'
+import json
+for l in open('gpurun_out/ops.jsonl'):
+    d=json.loads(l)
+    if any(k in d['op'] for k in ('concat','upsample','auto')): print(d['op'],'|',d['config'],'|',round(d['ms_per_launch']*1000,1),'us', d.get('hbm_frac'))
+P
+} > gpurun_out/round2.log 2>&1
+cat gpurun_out/round2.log
