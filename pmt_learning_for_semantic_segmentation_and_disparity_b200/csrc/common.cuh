@@ -94,6 +94,11 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   while (!mbar_try_wait(bar, parity)) {
   }
 }
+// Same, but a waiter that is not on the critical path sleeps between polls so that it does not compete with the
+// working warps for issue slots and for the shared-memory pipeline that serves mbarrier operations.
+__device__ __forceinline__ void mbar_wait_relaxed(uint64_t* bar, uint32_t parity, unsigned ns = 64) {
+  while (!mbar_try_wait(bar, parity)) __nanosleep(ns);
+}
 
 // TMA: 4-D tiled load global -> shared, completion on an mbarrier (SASS: UTMALDG).
 __device__ __forceinline__ void tma_load_4d(void* smem_dst, const CUtensorMap* map, int c0, int c1,

@@ -27,14 +27,24 @@ constexpr int kTM = 128;                  // output columns per tile (UMMA M)
 constexpr int kKC = 32;                   // band columns per K chunk (4 k-steps of 8)
 constexpr int kGdBytes = kTM * kKC * 4;   // 16 KB: one A-operand chunk
 constexpr int kEpiWarps = 4;
-// builder warps: the 3xTF32 build (hi + lo copies, band split) is latency-bound with 2 warps per scheduler, so it
-// gets 16 warps (measured 580 -> 540 us at the headline shape); the plain-TF32 build is lighter and keeps 8.
+// Builder warps.  The kernel is bound by instruction issue (ncu: ~2.5 warp-instructions per cycle per SM, most of it
+// the builders' address / predicate / handshake overhead, section 4.3 of DESIGN.md), so fewer, fatter warps win:
+// every builder warp pays the same fixed cost per chunk (barrier waits, tcgen05.st / fences, arrive, ring
+// bookkeeping), and 8 warps pay it half as often as 16 (measured 366 -> 341 us at the headline shape).
 template <int kPasses>
 struct BwdCfg {
-  static constexpr int kBuilders = kPasses == 3 ? 16 : 8;
-  // Every builder warp pays a fixed latency chain per chunk (barrier waits, tcgen05.st / fence, arrive), so the
-  // builders are split into two groups that take alternate chunks: the chain is paid every other chunk.
-  static constexpr int kGroups = 2;
+#ifndef PMT_BWD_BUILDERS3
+#define PMT_BWD_BUILDERS3 8
+#endif
+  static constexpr int kBuilders = kPasses == 3 ? PMT_BWD_BUILDERS3 : 8;
+  // The builders are split into groups that take chunks round-robin, so a group's latency chain (waits, build,
+  // fence, arrive) overlaps the other group's.  A group needs 4 warps (one per TMEM lane quarter).  More than 2
+  // groups would need as many A-operand slots in shared memory for gin2 (the parity-based waits tolerate at most
+  // one phase of lead per waiter), which do not fit.
+#ifndef PMT_BWD_GROUPS3
+#define PMT_BWD_GROUPS3 2
+#endif
+  static constexpr int kGroups = kPasses == 3 ? PMT_BWD_GROUPS3 : 2;
   static constexpr int kGroupWarps = kBuilders / kGroups;
   static constexpr int kThreads = 32 * (3 + kEpiWarps + kBuilders);  // band producer, MMA, 4 epilogue, builders, raw-g producer
 };
@@ -68,6 +78,7 @@ struct TcBwdArgs {
   int tmem_cols;
   int acc_cols;        // TMEM columns per accumulator (Cbox, or 2*Cbox for 3xTF32: hi and lo column blocks)
   TcBwdMode m[2];
+  int relax_ns;        // sleep between polls of the non-critical waiters (producers, epilogue); 0 = spin
   int debug;           // PMT_TC_DEBUG ablation bits: 4 skip Gd build, 32 skip band split, 16 skip MMA, 8 skip epilogue, 2048 / 4096 skip gin2 / gin1
 };
 
@@ -90,10 +101,24 @@ __device__ __forceinline__ float lo_tf32(float x) {
     mbar_wait(bar, par);                           \
     wait_cyc[slot] += clock64() - _t0;             \
   } while (0)
+#define PWAIT_RELAXED(slot, bar, par) PWAIT(slot, bar, par)
 #define PSEC_BEGIN() const long long _s0 = clock64()
 #define PSEC_END(slot) sec_cyc[slot] += clock64() - _s0
+// timeline trace of chunks [kTraceG0, kTraceG0+16) of the first CTA of each mode: prof[1024 + mode*1024 + role*128 + (g-G0)*8 + idx]
+#define kTraceG0 200
+#define PTRACE(role, g, idx)                                                                          \
+  do {                                                                                                \
+    if (prof != nullptr && cta_in_mode == 0 && lane == 0 && (g) >= kTraceG0 && (g) < kTraceG0 + 16)   \
+      prof[1024 + mode * 1024 + (role) * 128 + ((g) - kTraceG0) * 8 + (idx)] = clock64();             \
+  } while (0)
 #else
+#define PTRACE(role, g, idx)
 #define PWAIT(slot, bar, par) mbar_wait(bar, par)
+#define PWAIT_RELAXED(slot, bar, par)                    \
+  do {                                                   \
+    if (relax_ns) mbar_wait_relaxed(bar, par, relax_ns); \
+    else mbar_wait(bar, par);                            \
+  } while (0)
 #define PSEC_BEGIN()
 #define PSEC_END(slot)
 #endif
@@ -120,6 +145,7 @@ corr1d_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmIn1, const __grid_con
                      long long* __restrict__ prof) {
   constexpr int kBuilders = BwdCfg<kPasses>::kBuilders;
   constexpr int kGroupWarps = BwdCfg<kPasses>::kGroupWarps;
+  constexpr int kGroups = BwdCfg<kPasses>::kGroups;
   extern __shared__ __align__(1024) unsigned char smem[];
   uint64_t* band_full = reinterpret_cast<uint64_t*>(smem + a.bar_off);
   uint64_t* band_empty = band_full + kMaxBandSlots;
@@ -141,6 +167,7 @@ corr1d_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmIn1, const __grid_con
   float* __restrict__ dst = mode == 0 ? gin1 : gin2;
 
   const int tid = threadIdx.x, wid = tid >> 5, lane = tid & 31;
+  const unsigned relax_ns = (unsigned)a.relax_ns;
 #ifdef PMT_BWD_PROFILE
   long long wait_cyc[4] = {0, 0, 0, 0};
   long long sec_cyc[4] = {0, 0, 0, 0};
@@ -188,10 +215,15 @@ corr1d_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmIn1, const __grid_con
       for (int i = 0; i < n_my; ++i) {
         const TileCoord tc_ = tile_coord(a, i);
         for (int k = 0; k < a.NKC; ++k) {
-          PWAIT(0, &band_empty[bs], bph);
-          mbar_arrive_expect_tx(&band_full[bs], (uint32_t)band_bytes);
-          tma_load_4d(band_ring + (size_t)bs * a.band_slot_bytes, tmBand, tc_.x0 + m.oo + kKC * k, tc_.h, 0, tc_.n,
-                      &band_full[bs]);
+          PWAIT_RELAXED(0, &band_empty[bs], bph);
+          PTRACE(0, i * a.NKC + k, 0);
+          if (a.debug & 128) {   // ablation: no band traffic
+            mbar_arrive(&band_full[bs]);
+          } else {
+            mbar_arrive_expect_tx(&band_full[bs], (uint32_t)band_bytes);
+            tma_load_4d(band_ring + (size_t)bs * a.band_slot_bytes, tmBand, tc_.x0 + m.oo + kKC * k, tc_.h, 0, tc_.n,
+                        &band_full[bs]);
+          }
           if (++bs == m.band_slots) bs = 0, bph ^= 1u;
         }
       }
@@ -211,17 +243,25 @@ corr1d_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmIn1, const __grid_con
           if (mode == 0) {
             if (k < a.n_gboxes) {
               // the smem ring only reaches about one tile ahead: pull the next tile's box into L2 now
-              if (more) tma_prefetch_l2_4d(&tmG0, nx.x0, nx.h, 32 * k, nx.n);
-              PWAIT(0, &raw_empty[k], ((uint32_t)i & 1u) ^ 1u);  // previous tile is done with this box
-              mbar_arrive_expect_tx(&raw_full[k], (uint32_t)kBox0Bytes);
-              tma_load_4d(smem + k * kBox0Bytes, &tmG0, tc_.x0, tc_.h, 32 * k, tc_.n, &raw_full[k]);
+              if (more && !(a.debug & 64)) tma_prefetch_l2_4d(&tmG0, nx.x0, nx.h, 32 * k, nx.n);
+              PWAIT_RELAXED(0, &raw_empty[k], ((uint32_t)i & 1u) ^ 1u);  // previous tile is done with this box
+              if (a.debug & 64) {   // ablation: no raw-g traffic
+                mbar_arrive(&raw_full[k]);
+              } else {
+                mbar_arrive_expect_tx(&raw_full[k], (uint32_t)kBox0Bytes);
+                tma_load_4d(smem + k * kBox0Bytes, &tmG0, tc_.x0, tc_.h, 32 * k, tc_.n, &raw_full[k]);
+              }
             }
           } else {
             const int p0 = a.P - 1 + m.delta - kKC * k - (kKC - 1);
-            if (more) tma_prefetch_l2_4d(&tmG1, nx.x0 + m.oo + kKC * k, nx.h, p0, nx.n);
-            PWAIT(0, &raw_empty[slot], sph);
-            mbar_arrive_expect_tx(&raw_full[slot], (uint32_t)kRawSlot1);
-            tma_load_4d(smem + slot * kRawSlot1, &tmG1, tc_.x0 + m.oo + kKC * k, tc_.h, p0, tc_.n, &raw_full[slot]);
+            if (more && !(a.debug & 64)) tma_prefetch_l2_4d(&tmG1, nx.x0 + m.oo + kKC * k, nx.h, p0, nx.n);
+            PWAIT_RELAXED(0, &raw_empty[slot], sph);
+            if (a.debug & 64) {
+              mbar_arrive(&raw_full[slot]);
+            } else {
+              mbar_arrive_expect_tx(&raw_full[slot], (uint32_t)kRawSlot1);
+              tma_load_4d(smem + slot * kRawSlot1, &tmG1, tc_.x0 + m.oo + kKC * k, tc_.h, p0, tc_.n, &raw_full[slot]);
+            }
             if (++slot == kRawSlots1) slot = 0, sph ^= 1u;
           }
         }
@@ -248,8 +288,10 @@ corr1d_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmIn1, const __grid_con
         tc::fence_after_sync();
         const uint32_t d_tmem = tmem_base + (uint32_t)(buf * a.acc_cols);
         for (int k = 0; k < a.NKC; ++k) {
+          PTRACE(1, i * a.NKC + k, 0);
           PWAIT(1, &gd_built[gs], gph);
           if (kPasses == 1) PWAIT(2, &band_full[bs], bph);
+          PTRACE(1, i * a.NKC + k, 1);
           tc::fence_after_sync();
           const uint64_t dB = dB0 + (uint64_t)(b_step * (uint32_t)bs);
           { PSEC_BEGIN();
@@ -287,6 +329,7 @@ corr1d_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmIn1, const __grid_con
           tc::mma_commit(&gd_empty[gs]);
           tc::mma_commit(&band_empty[bs]);
           PSEC_END(1); }
+          PTRACE(1, i * a.NKC + k, 2);
           if (++gs == m.a_slots) gs = 0, gph ^= 1u;
           if (++bs == m.band_slots) bs = 0, bph ^= 1u;
         }
@@ -301,7 +344,7 @@ corr1d_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmIn1, const __grid_con
     for (int i = 0; i < n_my; ++i) {
       const int buf = i & 1;
       const TileCoord tc_ = tile_coord(a, i);
-      PWAIT(0, &tmem_full[buf], (uint32_t)(i >> 1) & 1u);
+      PWAIT_RELAXED(0, &tmem_full[buf], (uint32_t)(i >> 1) & 1u);
       tc::fence_after_sync();
       const bool ok = tc_.x0 + xl < a.W;
       float* o = dst + ((int64_t)tc_.n * a.C * a.H + tc_.h) * (int64_t)a.W + tc_.x0 + xl;
@@ -337,8 +380,8 @@ corr1d_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmIn1, const __grid_con
   } else {
     // ===== builder warps =====
     const int bw = wid - 2 - kEpiWarps;  // 0..kBuilders-1; consecutive warps cycle through the 4 TMEM lane quarters
-    const int grp = (bw >> 2) & 1;       // chunk parity this warp handles
-    const int gw = ((bw >> 2) >> 1) * 4 + (bw & 3);  // index inside the group, 0..kGroupWarps-1
+    const int grp = (bw >> 2) % kGroups;                  // this warp handles chunks g = grp (mod kGroups)
+    const int gw = ((bw >> 2) / kGroups) * 4 + (bw & 3);  // index inside the group, 0..kGroupWarps-1
     // running ring positions for the chunks this warp visits (g = grp, grp+2, ...): slot, and the phase parity seen
     // by a consumer-side wait (full/built); producer-side waits (empty) use the opposite parity
     int g = 0;
@@ -346,20 +389,23 @@ corr1d_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmIn1, const __grid_con
     uint32_t gph = (uint32_t)(grp / m.a_slots) & 1u, bph = (uint32_t)(grp / m.band_slots) & 1u,
              rph = (uint32_t)(grp / kRawSlots1) & 1u;
     auto advance2 = [](int& slot, uint32_t& ph, int n) {
-      slot += 2;
-      if (slot >= n) slot -= n, ph ^= 1u;   // ring sizes are even and >= 2
+      slot += kGroups;
+      while (slot >= n) slot -= n, ph ^= 1u;
     };
     for (int i = 0; i < n_my; ++i) {
       int boxes_ready = 0;
       int next_rel = 0;                  // mode 0: boxes are handed back to the producer in increasing order
       for (int k = 0; k < a.NKC; ++k, ++g) {
-        if ((g & 1) != grp) continue;
+        if (g % kGroups != grp) continue;
         unsigned char* sa = gd_ring + (size_t)gs * a.gd_slot_bytes;
         if (mode == 0) {
           // rows p <= 32k+31-delta are needed: boxes 0..k of this tile's [P][128] slice
           const int need = (k + 1 < a.n_gboxes) ? k + 1 : a.n_gboxes;
+          if (gw == 0) PTRACE(2 + grp, g, 0);
           while (boxes_ready < need) { PWAIT(0, &raw_full[boxes_ready], (uint32_t)i & 1u); ++boxes_ready; }
+          if (gw == 0) PTRACE(2 + grp, g, 1);
           PWAIT(1, &gd_empty[gs], gph ^ 1u);
+          if (gw == 0) PTRACE(2 + grp, g, 2);
           const float* Gt = reinterpret_cast<const float*>(smem);
           { PSEC_BEGIN();
           if (m.tmem_a) {
@@ -373,10 +419,14 @@ corr1d_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmIn1, const __grid_con
 #pragma unroll
             for (int c0 = 0; c0 < kCols; c0 += 16) {
               float w[16];
+              const float* col = Gt + xl;
+              const unsigned pu = (unsigned)(pb + c0), Pu = (unsigned)a.P;
 #pragma unroll
-              for (int t = 0; t < 16; ++t) {
-                const int p = pb + c0 + t;
-                w[t] = (p >= 0 && p < a.P && !(a.debug & 4)) ? Gt[p * kTM + xl] : 0.f;
+              for (int t = 0; t < 16; ++t)   // one unsigned compare covers p < 0 and p >= P
+                w[t] = (pu + (unsigned)t < Pu) ? col[(int)(pu + (unsigned)t) * kTM] : 0.f;
+              if (a.debug & 4) {
+#pragma unroll
+                for (int t = 0; t < 16; ++t) w[t] = 0.f;
               }
               tc::tmem_st16(ta + c0, w);
               if (kPasses == 3) {
@@ -408,23 +458,27 @@ corr1d_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmIn1, const __grid_con
             }
           }
           PSEC_END(0); }
+          if (gw == 0) PTRACE(2 + grp, g, 3);
           // hand back every box this warp will not read again (it visits chunks k, k+2, ...): box b is last used by
           // chunk min(NKC-1, b+koff), so it is dead for this warp once k >= that chunk - 1
           __syncwarp();
           if (lane == 0) {
-            const bool last_visit = k + 2 >= a.NKC;
+            const bool last_visit = k + kGroups >= a.NKC;
             while (next_rel < a.n_gboxes) {
               int kl = next_rel + m.koff;
               if (kl > a.NKC - 1) kl = a.NKC - 1;
-              if (!(kl <= k + 1 || last_visit)) break;
+              if (!(kl <= k + kGroups - 1 || last_visit)) break;
               mbar_arrive(&raw_empty[next_rel]);
               ++next_rel;
             }
           }
         } else {
           const int slot = rs;
+          if (gw == 0) PTRACE(2 + grp, g, 0);
           PWAIT(0, &raw_full[slot], rph);
+          if (gw == 0) PTRACE(2 + grp, g, 1);
           PWAIT(1, &gd_empty[gs], gph ^ 1u);
+          if (gw == 0) PTRACE(2 + grp, g, 2);
           const float* raw = reinterpret_cast<const float*>(smem + slot * kRawSlot1);
           { PSEC_BEGIN();
           if (!(a.debug & 4)) {
@@ -456,7 +510,9 @@ corr1d_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmIn1, const __grid_con
         }
         if (kPasses == 3) {
           // split the landed feature band chunk into hi / lo (position-wise, layout agnostic)
+          if (gw == 0) PTRACE(2 + grp, g, 4);
           PWAIT(2, &band_full[bs], bph);
+          if (gw == 0) PTRACE(2 + grp, g, 5);
           PSEC_BEGIN();
           unsigned char* sb = band_ring + (size_t)bs * a.band_slot_bytes;
           const int nch = band_bytes / 16;
@@ -482,6 +538,7 @@ corr1d_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmIn1, const __grid_con
         __syncwarp();
         if (lane == 0) mbar_arrive(&gd_built[gs]);
         PSEC_END(3); }
+        if (gw == 0) PTRACE(2 + grp, g, 6);
         advance2(gs, gph, m.a_slots);
         advance2(bs, bph, m.band_slots);
         advance2(rs, rph, kRawSlots1);
@@ -568,6 +625,8 @@ int fill_args(TcBwdArgs* a, int C, int H, int W, int P, int passes) {
   a->tmem_cols = cols;
   const char* dbg = getenv("PMT_TC_DEBUG");
   a->debug = dbg ? atoi(dbg) : 0;
+  const char* rx = getenv("PMT_BWD_RELAX_NS");
+  a->relax_ns = rx ? atoi(rx) : 64;
   return 0;
 }
 
@@ -601,7 +660,7 @@ int launch_corr1d_bwd_tc(const float* in1, const float* in2, const float* gout, 
   int64_t n_cta = 2 * tiles < sms ? 2 * tiles : sms;
   if (n_cta < 2) n_cta = 2;
   // measured optimum at the headline shape: 72 of 148 CTAs (3xTF32), 64 of 148 (plain TF32)
-  int n0 = (int)(n_cta * (a.m[0].tmem_a ? (passes == 3 ? 0.4865 : 0.432) : 0.5) + 0.5);
+  int n0 = (int)(n_cta * (a.m[0].tmem_a ? (passes == 3 ? 0.4865 : 0.4865) : 0.5) + 0.5);
   if (const char* e = getenv("PMT_BWD_SPLIT")) n0 = atoi(e);  // tuning knob
   if (n0 < 1) n0 = 1;
   if (n0 > n_cta - 1) n0 = (int)n_cta - 1;
