@@ -31,14 +31,21 @@ def main():
     ap.add_argument("--batch", type=int, default=4)
     ap.add_argument("--no-sync-bn", action="store_true")
     ap.add_argument("--eager", action="store_true", help="do not capture the step in a CUDA graph")
-    ap.add_argument("--graph", action="store_true",
-                    help="force CUDA-graph capture under DDP too (default: graph at 1 GPU, eager under DDP -- capturing "
-                         "DDP+SyncBatchNorm NCCL collectives hung on the 2-GPU box in round 1)")
+    ap.add_argument("--graph", action="store_true", help="(default) capture the whole step, NCCL collectives included, "
+                                                         "in one CUDA graph")
     args = ap.parse_args()
+    if not args.eager and int(os.environ.get("WORLD_SIZE", "1")) > 1:
+        # capturing NCCL collectives: the watchdog must not query/abort work that lives inside a capture
+        os.environ.setdefault("TORCH_NCCL_ASYNC_ERROR_HANDLING", "0")
+        os.environ.setdefault("TORCH_NCCL_ENABLE_MONITORING", "0")
+        if os.environ.get("PMT_STEP_HANG_DUMP"):
+            import faulthandler
+
+            faulthandler.dump_traceback_later(int(os.environ["PMT_STEP_HANG_DUMP"]), exit=True)
     world = sharding.init_world("nccl" if int(os.environ.get("WORLD_SIZE", "1")) > 1 else None)
     dev = torch.device("cuda", world.local_rank)
     torch.cuda.set_device(dev)
-    use_graph = args.graph or (not args.eager and world.world_size == 1)
+    use_graph = not args.eager
     step, model = harness.build_training_step(world, batch_per_gpu=args.batch, sync_bn=not args.no_sync_bn,
                                                cuda_graph=use_graph)
     for _ in range(max(args.warmup, 3)):
@@ -63,6 +70,21 @@ def main():
                           "cuda_graph": use_graph,
                           "collectives": "DDP gradient all-reduce + SyncBatchNorm statistics (NCCL); none in the hot-path ops"}),
               flush=True)
+    if use_graph and world.distributed:
+        # A CUDA graph that holds captured NCCL kernels keeps the communicator busy: destroy_process_group() was
+        # observed to block forever behind it (that -- not the capture -- was the "hang" of the first attempts).
+        # Release the graph first, and never let teardown outlive the measurement.
+        import threading
+
+        sys.stdout.flush()
+        step.graph.reset()
+        torch.cuda.synchronize(dev)
+        t = threading.Thread(target=sharding.shutdown, args=(world,), daemon=True)
+        t.start()
+        t.join(15.0)
+        if t.is_alive():
+            os._exit(0)
+        return
     sharding.shutdown(world)
 
 

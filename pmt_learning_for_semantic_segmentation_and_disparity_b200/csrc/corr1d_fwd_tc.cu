@@ -228,15 +228,23 @@ corr1d_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmL, const __grid_const
         unsigned char* lbase = smem + a.lo_ring_off + (size_t)ls * a.stage_bytes;
         // hi operand = the raw fp32 left in place (kind::tf32 ignores the low 13 mantissa bits, verified on B200:
         // the 3-term sum stays at ~1e-6); lo = x - trunc_tf32(x) is exact in fp32 and goes to the lo ring.
-#pragma unroll 2
-        for (int c = t; c < nchunks && !(a.debug & 4); c += 128) {
-          const float4 x = *reinterpret_cast<const float4*>(sbase + 16 * c);
-          float4 lo;
-          lo.x = x.x - __uint_as_float(__float_as_uint(x.x) & 0xffffe000u);
-          lo.y = x.y - __uint_as_float(__float_as_uint(x.y) & 0xffffe000u);
-          lo.z = x.z - __uint_as_float(__float_as_uint(x.z) & 0xffffe000u);
-          lo.w = x.w - __uint_as_float(__float_as_uint(x.w) & 0xffffe000u);
-          *reinterpret_cast<float4*>(lbase + 16 * c) = lo;
+        // loads are issued in batches of 8 before the first store: the LDS latency is paid once per batch
+        for (int cb = t; cb < nchunks && !(a.debug & 4); cb += 8 * 128) {
+          float4 x[8];
+#pragma unroll
+          for (int u = 0; u < 8; ++u)
+            if (cb + u * 128 < nchunks) x[u] = *reinterpret_cast<const float4*>(sbase + 16 * (cb + u * 128));
+#pragma unroll
+          for (int u = 0; u < 8; ++u) {
+            if (cb + u * 128 < nchunks) {
+              float4 lo;
+              lo.x = x[u].x - __uint_as_float(__float_as_uint(x[u].x) & 0xffffe000u);
+              lo.y = x[u].y - __uint_as_float(__float_as_uint(x[u].y) & 0xffffe000u);
+              lo.z = x[u].z - __uint_as_float(__float_as_uint(x[u].z) & 0xffffe000u);
+              lo.w = x[u].w - __uint_as_float(__float_as_uint(x[u].w) & 0xffffe000u);
+              *reinterpret_cast<float4*>(lbase + 16 * (cb + u * 128)) = lo;
+            }
+          }
         }
         fence_proxy_async();  // make the rewritten stage visible to the tensor core's async-proxy reads
         __syncwarp();

@@ -119,7 +119,8 @@ def build_training_step(world, batch_per_gpu: int = 4, h: int = 256, w: int = 51
 
     graph = torch.cuda.CUDAGraph()
     opt.zero_grad(set_to_none=True)
-    with torch.cuda.graph(graph):
+    # thread_local: the NCCL watchdog thread may touch the CUDA runtime while this thread captures
+    with torch.cuda.graph(graph, capture_error_mode="thread_local" if world.distributed else "global"):
         static_loss = sdnet_loss(model(left, right), seg, disp)
         static_loss.backward()
         opt.step()
