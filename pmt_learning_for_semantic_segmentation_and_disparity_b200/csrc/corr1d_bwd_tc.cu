@@ -27,31 +27,23 @@ constexpr int kTM = 128;                  // output columns per tile (UMMA M)
 constexpr int kKC = 32;                   // band columns per K chunk (4 k-steps of 8)
 constexpr int kGdBytes = kTM * kKC * 4;   // 16 KB: one A-operand chunk
 constexpr int kEpiWarps = 4;
-// Builder warps.  The kernel is bound by instruction issue (ncu: ~2.5 warp-instructions per cycle per SM, most of it
-// the builders' address / predicate / handshake overhead, section 4.3 of DESIGN.md), so fewer, fatter warps win:
-// every builder warp pays the same fixed cost per chunk (barrier waits, tcgen05.st / fences, arrive, ring
-// bookkeeping), and 8 warps pay it half as often as 16 (measured 366 -> 341 us at the headline shape).
-template <int kPasses>
+// Builder warps.  Every builder warp pays a fixed cost per chunk (barrier waits, tcgen05.st / fences, arrive, ring
+// bookkeeping) on top of the elements it moves, so few, fat warps win over many thin ones (16 -> 8 warps: 366 -> 341 us
+// at the headline shape, issue-slot utilisation 64% -> 47%).  The builders work in groups of 4 warps (one per TMEM lane
+// quarter) that take chunks round-robin, so a group's latency chain (waits, build, fence, arrive) overlaps the other
+// groups'.  Every ring a group waits on needs one slot per group (parity waits tolerate one phase of lead per waiter),
+// so 3 groups are used when 3 shared-memory A-operand slots fit for gin2 (C <= 64: 345 -> 333 us), else 2.
+template <int kPasses, int kGroups_>
 struct BwdCfg {
-#ifndef PMT_BWD_BUILDERS3
-#define PMT_BWD_BUILDERS3 8
-#endif
-  static constexpr int kBuilders = kPasses == 3 ? PMT_BWD_BUILDERS3 : 8;
-  // The builders are split into groups that take chunks round-robin, so a group's latency chain (waits, build,
-  // fence, arrive) overlaps the other group's.  A group needs 4 warps (one per TMEM lane quarter).  More than 2
-  // groups would need as many A-operand slots in shared memory for gin2 (the parity-based waits tolerate at most
-  // one phase of lead per waiter), which do not fit.
-#ifndef PMT_BWD_GROUPS3
-#define PMT_BWD_GROUPS3 2
-#endif
-  static constexpr int kGroups = kPasses == 3 ? PMT_BWD_GROUPS3 : 2;
-  static constexpr int kGroupWarps = kBuilders / kGroups;
+  static constexpr int kGroups = kGroups_;
+  static constexpr int kGroupWarps = 4;
+  static constexpr int kBuilders = kGroupWarps * kGroups;
   static constexpr int kThreads = 32 * (3 + kEpiWarps + kBuilders);  // band producer, MMA, 4 epilogue, builders, raw-g producer
 };
 constexpr int kBox0Bytes = 32 * kTM * 4;          // mode 0: 32 rows of g x 128 columns (16 KB)
 constexpr int kRawRows1 = 160;                    // mode 1: rows of a raw block (>= 128+32-1)
 constexpr int kRawSlot1 = kRawRows1 * kKC * 4;    // 20 KB
-constexpr int kRawSlots1 = 4;
+constexpr int kMaxRawSlots1 = 4;
 constexpr int kMaxBandSlots = 8, kMaxGdSlots = 4;
 
 struct TcBwdMode {
@@ -62,6 +54,8 @@ struct TcBwdMode {
   int band_slots;  // band ring depth
   int band_off;    // byte offset of the band ring
   int tmem_a;      // 1: Gd chunks are written straight into TMEM (tcgen05.st) and the MMA takes A from TMEM
+  int gd_off;      // byte offset of the shared-memory Gd ring (mode 1)
+  int raw_slots;   // mode 1: raw-g ring depth
 };
 
 struct TcBwdArgs {
@@ -74,7 +68,7 @@ struct TcBwdArgs {
   int a_base, aslot_cols;  // TMEM A ring: first column, columns per slot (32 hi [+ 32 lo])
   int gd_slot_bytes, gd_lo_off;       // Gd ring slot: hi [16 KB] (+ lo [16 KB])
   int band_slot_bytes, band_lo_off;   // band ring slot: hi [Cbox*128] (+ lo)
-  int gd_off, bar_off;                // byte offsets in dynamic shared memory (raw ring at 0)
+  int bar_off;                        // byte offset of the mbarriers in dynamic shared memory (raw ring at 0)
   int tmem_cols;
   int acc_cols;        // TMEM columns per accumulator (Cbox, or 2*Cbox for 3xTF32: hi and lo column blocks)
   TcBwdMode m[2];
@@ -137,15 +131,14 @@ __device__ __forceinline__ TileCoord tile_coord(const TcBwdArgs& a, int i) {
   return c;
 }
 
-template <int kPasses>
-__global__ void __launch_bounds__(BwdCfg<kPasses>::kThreads, 1)
+template <int kPasses, int kGroups>
+__global__ void __launch_bounds__(BwdCfg<kPasses, kGroups>::kThreads, 1)
 corr1d_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmIn1, const __grid_constant__ CUtensorMap tmIn2,
                      const __grid_constant__ CUtensorMap tmG0, const __grid_constant__ CUtensorMap tmG1,
                      float* __restrict__ gin1, float* __restrict__ gin2, const TcBwdArgs a,
                      long long* __restrict__ prof) {
-  constexpr int kBuilders = BwdCfg<kPasses>::kBuilders;
-  constexpr int kGroupWarps = BwdCfg<kPasses>::kGroupWarps;
-  constexpr int kGroups = BwdCfg<kPasses>::kGroups;
+  constexpr int kBuilders = BwdCfg<kPasses, kGroups>::kBuilders;
+  constexpr int kGroupWarps = BwdCfg<kPasses, kGroups>::kGroupWarps;
   extern __shared__ __align__(1024) unsigned char smem[];
   uint64_t* band_full = reinterpret_cast<uint64_t*>(smem + a.bar_off);
   uint64_t* band_empty = band_full + kMaxBandSlots;
@@ -156,13 +149,14 @@ corr1d_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmIn1, const __grid_con
   uint64_t* tmem_full = raw_empty + 8;
   uint64_t* tmem_empty = tmem_full + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
-  unsigned char* gd_ring = smem + a.gd_off;
+
 
   const int mode = (int)blockIdx.x < a.n_cta0 ? 0 : 1;
   const int cta_in_mode = mode == 0 ? (int)blockIdx.x : (int)blockIdx.x - a.n_cta0;
   const int ctas_of_mode = mode == 0 ? a.n_cta0 : (int)gridDim.x - a.n_cta0;
   const TcBwdMode m = a.m[mode];
   unsigned char* band_ring = smem + m.band_off;
+  unsigned char* gd_ring = smem + m.gd_off;
   const CUtensorMap* tmBand = mode == 0 ? &tmIn2 : &tmIn1;
   float* __restrict__ dst = mode == 0 ? gin1 : gin2;
 
@@ -262,7 +256,7 @@ corr1d_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmIn1, const __grid_con
               mbar_arrive_expect_tx(&raw_full[slot], (uint32_t)kRawSlot1);
               tma_load_4d(smem + slot * kRawSlot1, &tmG1, tc_.x0 + m.oo + kKC * k, tc_.h, p0, tc_.n, &raw_full[slot]);
             }
-            if (++slot == kRawSlots1) slot = 0, sph ^= 1u;
+            if (++slot == m.raw_slots) slot = 0, sph ^= 1u;
           }
         }
       }
@@ -385,9 +379,9 @@ corr1d_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmIn1, const __grid_con
     // running ring positions for the chunks this warp visits (g = grp, grp+2, ...): slot, and the phase parity seen
     // by a consumer-side wait (full/built); producer-side waits (empty) use the opposite parity
     int g = 0;
-    int gs = grp % m.a_slots, bs = grp % m.band_slots, rs = grp % kRawSlots1;
+    int gs = grp % m.a_slots, bs = grp % m.band_slots, rs = grp % m.raw_slots;
     uint32_t gph = (uint32_t)(grp / m.a_slots) & 1u, bph = (uint32_t)(grp / m.band_slots) & 1u,
-             rph = (uint32_t)(grp / kRawSlots1) & 1u;
+             rph = (uint32_t)(grp / m.raw_slots) & 1u;
     auto advance2 = [](int& slot, uint32_t& ph, int n) {
       slot += kGroups;
       while (slot >= n) slot -= n, ph ^= 1u;
@@ -541,7 +535,7 @@ corr1d_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmIn1, const __grid_con
         if (gw == 0) PTRACE(2 + grp, g, 6);
         advance2(gs, gph, m.a_slots);
         advance2(bs, bph, m.band_slots);
-        advance2(rs, rph, kRawSlots1);
+        advance2(rs, rph, m.raw_slots);
       }
     }
   }
@@ -562,7 +556,7 @@ corr1d_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmIn1, const __grid_con
   }
 }
 
-int fill_args(TcBwdArgs* a, int C, int H, int W, int P, int passes) {
+int fill_args(TcBwdArgs* a, int C, int H, int W, int P, int passes, int groups) {
   a->C = C, a->H = H, a->W = W, a->P = P, a->rW = (P - 1) / 2;
   if (C > 128) return 1;
   a->Cbox = round_up(C, 32);  // the epilogue reads TMEM in 32-column groups; UMMA N % 16 == 0
@@ -579,8 +573,7 @@ int fill_args(TcBwdArgs* a, int C, int H, int W, int P, int passes) {
   a->n_tiles = 0;  // set by the launcher (needs B)
   a->n_gboxes = ceil_div(P, 32);
   if (a->n_gboxes > 8) return 1;
-  const int raw0 = a->n_gboxes * kBox0Bytes, raw1 = kRawSlots1 * kRawSlot1;
-  const int raw_bytes = round_up(raw0 > raw1 ? raw0 : raw1, 1024);
+  const int raw0 = a->n_gboxes * kBox0Bytes;
   const int mult = passes == 3 ? 2 : 1;
   a->gd_lo_off = kGdBytes;
   a->gd_slot_bytes = kGdBytes * mult;
@@ -588,7 +581,6 @@ int fill_args(TcBwdArgs* a, int C, int H, int W, int P, int passes) {
   a->band_slot_bytes = a->Cbox * 128 * mult;
   a->acc_cols = a->Cbox * mult;                 // 3xTF32 keeps two column blocks per accumulator
   if (2 * a->acc_cols > 512) return 1;
-  a->gd_off = raw_bytes;
   const int smem_budget = 227 * 1024 - 1024;
   // A operand in TMEM (mode 0 only -- its Gd rows are conflict-free column reads of the resident g slice): needs
   // columns next to the two accumulators.
@@ -596,24 +588,30 @@ int fill_args(TcBwdArgs* a, int C, int H, int W, int P, int passes) {
   a->a_base = 2 * a->acc_cols;
   int tmem_slots = (512 - a->a_base) / a->aslot_cols;
   if (tmem_slots > kMaxGdSlots) tmem_slots = kMaxGdSlots;
-  tmem_slots &= ~1;                             // even: a slot is always revisited by the same builder group
   const bool want_tmem_a = getenv("PMT_NO_TMEM_A") == nullptr;
   int max_end = 0;
   for (int md = 0; md < 2; ++md) {
     TcBwdMode& m = a->m[md];
-    m.tmem_a = (md == 0 && want_tmem_a && tmem_slots >= 2) ? 1 : 0;
+    // every ring a builder group waits on needs at least one slot per group (parity waits tolerate one phase of lead)
+    m.tmem_a = (md == 0 && want_tmem_a && tmem_slots >= groups) ? 1 : 0;
     int gd_bytes = 0;
+    if (md == 0) {
+      m.raw_slots = a->n_gboxes;
+      m.gd_off = round_up(raw0, 1024);
+    } else {
+      m.raw_slots = groups < 3 ? kMaxRawSlots1 : groups;   // 3 groups: 3 raw + 3 Gd slots fit, 4 + 3 do not
+      m.gd_off = round_up(m.raw_slots * kRawSlot1, 1024);
+    }
     if (m.tmem_a) {
       m.a_slots = tmem_slots;
     } else {
-      m.a_slots = 2;
+      m.a_slots = groups;
       gd_bytes = m.a_slots * a->gd_slot_bytes;
     }
-    m.band_off = a->gd_off + gd_bytes;
+    m.band_off = m.gd_off + gd_bytes;
     int bslots = (smem_budget - m.band_off) / a->band_slot_bytes;
     if (bslots > kMaxBandSlots) bslots = kMaxBandSlots;
-    bslots &= ~1;
-    if (bslots < 2) return 1;
+    if (bslots < groups) return 1;
     m.band_slots = bslots;
     const int end = m.band_off + bslots * a->band_slot_bytes;
     if (end > max_end) max_end = end;
@@ -635,7 +633,7 @@ int fill_args(TcBwdArgs* a, int C, int H, int W, int P, int passes) {
 bool corr1d_bwd_tc_ok(const void* in1, const void* in2, int C, int H, int W, int P, int dilp, int passes) {
   if (dilp != 1 || P < 1 || C < 1 || W % 4 != 0 || !aligned16(in1) || !aligned16(in2)) return false;
   TcBwdArgs a;
-  return fill_args(&a, C, H, W, P, passes) == 0;
+  return fill_args(&a, C, H, W, P, passes, 2) == 0;
 }
 
 long long* g_bwd_prof = nullptr;  // device buffer for PMT_BWD_PROFILE builds (set through pmt_debug_set_ptr)
@@ -644,7 +642,10 @@ int launch_corr1d_bwd_tc(const float* in1, const float* in2, const float* gout, 
                          int C, int H, int W, int P, int passes, cudaStream_t st) {
   TcBwdArgs a;
   PMT_CHECK_ARG(passes == 1 || passes == 3, "corr1d tc: passes must be 1 (tf32) or 3 (3xtf32)");
-  PMT_CHECK_ARG(fill_args(&a, C, H, W, P, passes) == 0, "corr1d tc bwd: unsupported shape C=%d P=%d", C, P);
+  int groups = passes == 3 ? 3 : 2;   // 3xTF32: 3 builder groups when their shared-memory rings fit, else 2
+  if (const char* e = getenv("PMT_BWD_GROUPS")) groups = atoi(e) == 2 ? 2 : 3;
+  if (fill_args(&a, C, H, W, P, passes, groups) != 0) groups = 2;
+  PMT_CHECK_ARG(fill_args(&a, C, H, W, P, passes, groups) == 0, "corr1d tc bwd: unsupported shape C=%d P=%d", C, P);
   CUtensorMap tm1, tm2, tmG0, tmG1;
   if (int e = make_tmap_nchw_ex(&tm1, in1, B, C, H, W, kKC, a.Cbox, 1)) return e;
   if (int e = make_tmap_nchw_ex(&tm2, in2, B, C, H, W, kKC, a.Cbox, 1)) return e;
@@ -659,19 +660,27 @@ int launch_corr1d_bwd_tc(const float* in1, const float* in2, const float* gout, 
   const int sms = sm_count();
   int64_t n_cta = 2 * tiles < sms ? 2 * tiles : sms;
   if (n_cta < 2) n_cta = 2;
-  // measured optimum at the headline shape: 72 of 148 CTAs (3xTF32), 64 of 148 (plain TF32)
-  int n0 = (int)(n_cta * (a.m[0].tmem_a ? (passes == 3 ? 0.4865 : 0.4865) : 0.5) + 0.5);
+  // measured optimum at the headline shape: an even split with 3 builder groups, 72 of 148 with 2
+  int n0 = (int)(n_cta * (a.m[0].tmem_a && groups == 2 && passes == 3 ? 0.4865 : 0.5) + 0.5);
   if (const char* e = getenv("PMT_BWD_SPLIT")) n0 = atoi(e);  // tuning knob
   if (n0 < 1) n0 = 1;
   if (n0 > n_cta - 1) n0 = (int)n_cta - 1;
   a.n_cta0 = n0;
+#define PMT_LAUNCH_BWD(PASSES, GROUPS)                                                                              \
+  do {                                                                                                              \
+    PMT_CUDA_OK(cudaFuncSetAttribute(corr1d_bwd_tc_kernel<PASSES, GROUPS>,                                          \
+                                     cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));                     \
+    corr1d_bwd_tc_kernel<PASSES, GROUPS><<<dim3((unsigned)n_cta), BwdCfg<PASSES, GROUPS>::kThreads, smem_bytes, st>>>( \
+        tm1, tm2, tmG0, tmG1, gin1, gin2, a, g_bwd_prof);                                                           \
+  } while (0)
   if (passes == 3) {
-    PMT_CUDA_OK(cudaFuncSetAttribute(corr1d_bwd_tc_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
-    corr1d_bwd_tc_kernel<3><<<dim3((unsigned)n_cta), BwdCfg<3>::kThreads, smem_bytes, st>>>(tm1, tm2, tmG0, tmG1, gin1, gin2, a, g_bwd_prof);
+    if (groups == 3) PMT_LAUNCH_BWD(3, 3);
+    else PMT_LAUNCH_BWD(3, 2);
   } else {
-    PMT_CUDA_OK(cudaFuncSetAttribute(corr1d_bwd_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
-    corr1d_bwd_tc_kernel<1><<<dim3((unsigned)n_cta), BwdCfg<1>::kThreads, smem_bytes, st>>>(tm1, tm2, tmG0, tmG1, gin1, gin2, a, g_bwd_prof);
+    if (groups == 3) PMT_LAUNCH_BWD(1, 3);
+    else PMT_LAUNCH_BWD(1, 2);
   }
+#undef PMT_LAUNCH_BWD
   PMT_LAUNCH_OK("corr1d_bwd_tc_kernel");
   return PMT_OK;
 }
