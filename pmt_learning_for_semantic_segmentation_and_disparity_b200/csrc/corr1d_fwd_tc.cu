@@ -26,7 +26,7 @@ constexpr int kCK = 16;               // channels per ring stage (2 k-steps of 8
 constexpr int kBoxBytes = kCK * 128;  // one 32-column x 16-channel box
 constexpr int kLBlocks = kTM / 32;    // 4 boxes for the L tile
 constexpr int kMaxNB = 10;            // band boxes (P <= 193)
-constexpr int kRowsPerStep = 48;      // output planes per staging buffer / TMA store
+constexpr int kRowsPerStep = 32;      // output planes per staging buffer / TMA store (= one TMEM column block)
 constexpr int kStepBytes = kRowsPerStep * kTM * 4;
 
 struct TcFwdArgs {
@@ -181,34 +181,39 @@ corr1d_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmL, const __grid_const
       const int wt = tile % a.n_wtiles, h = (tile / a.n_wtiles) % a.H, n = tile / (a.n_wtiles * a.H);
       mbar_wait(tmem_full, (uint32_t)it & 1u);
       tc::fence_after_sync();
-      // kRowsPerStep output planes at a time through two ping-pong staging buffers, one TMA store per step
+      // 32 output planes per step through two ping-pong staging buffers, one TMA store per step.  TMEM is read in
+      // 32-column blocks that start at column delta, so that block b holds, for lane w = 32q+lane, the planes
+      // p = 32(b-q) + jj - lane (jj = column inside the block): the planes [32s, 32s+32) of this warp's 32 output
+      // columns are the upper triangle (jj >= lane) of block s+q and the lower triangle (jj < lane) of block s+q+1.
+      // Every block is therefore loaded from TMEM exactly once and kept in registers for the following step
+      // (TMEM reads, 64 B/clk, were the longest part of the drain when every block was fetched for two steps).
+      float vp[32], vc[32];
+      tc::tmem_ld32(tmem_base + ((uint32_t)(32 * q) << 16) + (uint32_t)(32 * q + a.delta), vp);
+      const int r0 = (32 - lane) & 31;
       for (int s = 0; s < a.n_steps; ++s, ++gstep) {
         float* tile_s = reinterpret_cast<float*>(smem + a.tile_off + (gstep & 1) * kStepBytes);
-        const int p0 = kRowsPerStep * s;
-        if (wid == 2 && lane == 0) tc::tma_store_wait_read<1>();  // the store that last used this buffer has read it
-        named_bar_sync(1, 128);
-        const int c_lo = (p0 + a.delta + 32 * q) / 32;
-        int c_hi = (p0 + kRowsPerStep - 1 + a.delta + 32 * q + 31) / 32;
-        if (c_hi > a.NB - 1) c_hi = a.NB - 1;
-        for (int cb = c_lo; cb <= c_hi && !(a.debug & 8); ++cb) {
-          float v[32];
-          tc::tmem_ld32(tmem_base + ((uint32_t)(32 * q) << 16) + (uint32_t)(32 * cb), v);
-          const int pbase = 32 * cb - a.delta - wl - p0;  // plane (relative to p0) of column jj is pbase + jj
-#pragma unroll
-          for (int jj = 0; jj < 32; ++jj) {
-            const int pr = pbase + jj;
-            if (pr >= 0 && pr < kRowsPerStep && p0 + pr < a.P) tile_s[pr * kTM + wl] = v[jj];
-          }
-        }
+        tc::tmem_ld32(tmem_base + ((uint32_t)(32 * q) << 16) + (uint32_t)(32 * (s + q + 1) + a.delta), vc);
         if (s == a.n_steps - 1) {
           tc::fence_before_sync();
           __syncwarp();
           if (lane == 0) mbar_arrive(tmem_empty);  // TMEM drained: the next tile's MMAs may start
         }
+        if (wid == 2 && lane == 0) tc::tma_store_wait_read<1>();  // the store that last used this buffer has read it
+        named_bar_sync(1, 128);
+        if (!(a.debug & 8)) {
+          float* col = tile_s + wl;
+#pragma unroll
+          for (int jj = 0; jj < 32; ++jj) {
+            const float v = (jj >= lane) ? vp[jj] : vc[jj];
+            col[((r0 + jj) & 31) * kTM] = v;       // staging row = plane - 32s = (jj - lane) mod 32
+          }
+        }
+#pragma unroll
+        for (int jj = 0; jj < 32; ++jj) vp[jj] = vc[jj];
         fence_proxy_async();                       // generic-proxy writes -> visible to the TMA store
         named_bar_sync(1, 128);
         if (wid == 2 && lane == 0) {
-          tc::tma_store_4d(&tmO, tile_s, wt * kTM, h, p0, n);
+          tc::tma_store_4d(&tmO, tile_s, wt * kTM, h, kRowsPerStep * s, n);
           tc::tma_store_commit();
         }
       }
@@ -271,18 +276,21 @@ int fill_args(TcFwdArgs* a, int C, int H, int W, int P, int passes) {
   const int nb1 = (a->NB + 1) / 2;
   a->N1 = 32 * nb1;
   a->N2 = 32 * (a->NB - nb1);
+  a->n_steps = ceil_div(P, kRowsPerStep);
   int cols = 32;
-  while (cols < 32 * a->NB) cols *= 2;
+  const int last_col = 32 * (a->n_steps + 4) + a->delta + 32;   // the epilogue reads blocks 0 .. n_steps+3, shifted by delta
+  while (cols < 32 * a->NB || cols < last_col) cols *= 2;
+  if (cols > 512) return 1;
   a->tmem_cols = cols;
   a->n_wtiles = ceil_div(W, kTM);
   a->n_cchunks = ceil_div(C, kCK);
   a->n_tiles = 0;  // set by the launcher (needs B)
   a->stage_bytes = (kLBlocks + a->NB) * kBoxBytes;
-  a->n_steps = ceil_div(P, kRowsPerStep);
   const int budget = 227 * 1024 - 1024 - 2 * kStepBytes;
   int total = budget / a->stage_bytes;  // ring stages that fit next to the two staging buffers
   if (passes == 3) {
-    a->lo_stages = total >= 6 ? 2 : 1;
+    a->lo_stages = total >= 6 ? 2 : 1;   // measured at the headline shape (7 stages): 5 raw + 2 lo beats 4 + 3
+    if (const char* e = getenv("PMT_FWD_LO_STAGES")) a->lo_stages = atoi(e);
     a->stages = total - a->lo_stages;
   } else {
     a->lo_stages = 1;
