@@ -31,6 +31,9 @@ def main():
     ap.add_argument("--batch", type=int, default=4)
     ap.add_argument("--no-sync-bn", action="store_true")
     ap.add_argument("--eager", action="store_true", help="do not capture the step in a CUDA graph")
+    ap.add_argument("--no-pair", action="store_true",
+                    help="run the siamese tower twice (one SyncBatchNorm collective per call) instead of once over "
+                         "[left; right] with per-half statistics and one collective per layer")
     ap.add_argument("--graph", action="store_true", help="(default) capture the whole step, NCCL collectives included, "
                                                          "in one CUDA graph")
     args = ap.parse_args()
@@ -47,7 +50,7 @@ def main():
     torch.cuda.set_device(dev)
     use_graph = not args.eager
     step, model = harness.build_training_step(world, batch_per_gpu=args.batch, sync_bn=not args.no_sync_bn,
-                                               cuda_graph=use_graph)
+                                               cuda_graph=use_graph, paired_tower=not args.no_pair)
     for _ in range(max(args.warmup, 3)):
         loss = step()
     torch.cuda.synchronize(dev)
@@ -67,7 +70,7 @@ def main():
                           "unit": "pairs/s", "n_gpus": world.world_size, "steps": args.steps,
                           "ms_per_step": ms / args.steps, "scaling": "weak", "global_batch": args.batch * world.world_size,
                           "params": n_params, "loss": float(loss.detach()), "sync_bn": not args.no_sync_bn,
-                          "cuda_graph": use_graph,
+                          "cuda_graph": use_graph, "paired_tower": not args.no_pair and not args.no_sync_bn,
                           "collectives": "DDP gradient all-reduce + SyncBatchNorm statistics (NCCL); none in the hot-path ops"}),
               flush=True)
     if use_graph and world.distributed:

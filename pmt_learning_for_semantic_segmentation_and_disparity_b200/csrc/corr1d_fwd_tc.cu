@@ -41,6 +41,7 @@ struct TcFwdArgs {
   int lo_ring_off;       // byte offset of the lo ring
   int tile_off;          // byte offset of the two [48][128] staging buffers
   int n_steps;           // epilogue steps of kRowsPerStep output planes
+  int n_bufs;            // staging buffers (2 or 3)
   int bar_off;           // byte offset of the barriers
   int debug;             // PMT_TC_DEBUG: 1 = constant tile, 2 = tcgen05.st pattern instead of MMA result
 };
@@ -191,14 +192,17 @@ corr1d_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmL, const __grid_const
       tc::tmem_ld32(tmem_base + ((uint32_t)(32 * q) << 16) + (uint32_t)(32 * q + a.delta), vp);
       const int r0 = (32 - lane) & 31;
       for (int s = 0; s < a.n_steps; ++s, ++gstep) {
-        float* tile_s = reinterpret_cast<float*>(smem + a.tile_off + (gstep & 1) * kStepBytes);
+        float* tile_s = reinterpret_cast<float*>(smem + a.tile_off + (gstep % a.n_bufs) * kStepBytes);
         tc::tmem_ld32(tmem_base + ((uint32_t)(32 * q) << 16) + (uint32_t)(32 * (s + q + 1) + a.delta), vc);
         if (s == a.n_steps - 1) {
           tc::fence_before_sync();
           __syncwarp();
           if (lane == 0) mbar_arrive(tmem_empty);  // TMEM drained: the next tile's MMAs may start
         }
-        if (wid == 2 && lane == 0) tc::tma_store_wait_read<1>();  // the store that last used this buffer has read it
+        if (wid == 2 && lane == 0) {   // the store that last used this buffer has read it
+          if (a.n_bufs == 3) tc::tma_store_wait_read<2>();
+          else tc::tma_store_wait_read<1>();
+        }
         named_bar_sync(1, 128);
         if (!(a.debug & 8)) {
           float* col = tile_s + wl;
@@ -286,7 +290,9 @@ int fill_args(TcFwdArgs* a, int C, int H, int W, int P, int passes) {
   a->n_cchunks = ceil_div(C, kCK);
   a->n_tiles = 0;  // set by the launcher (needs B)
   a->stage_bytes = (kLBlocks + a->NB) * kBoxBytes;
-  const int budget = 227 * 1024 - 1024 - 2 * kStepBytes;
+  a->n_bufs = 2;
+  if (const char* e = getenv("PMT_FWD_NBUF")) a->n_bufs = atoi(e) == 3 ? 3 : 2;
+  const int budget = 227 * 1024 - 1024 - a->n_bufs * kStepBytes;
   int total = budget / a->stage_bytes;  // ring stages that fit next to the two staging buffers
   if (passes == 3) {
     a->lo_stages = total >= 6 ? 2 : 1;   // measured at the headline shape (7 stages): 5 raw + 2 lo beats 4 + 3
@@ -300,7 +306,7 @@ int fill_args(TcFwdArgs* a, int C, int H, int W, int P, int passes) {
   if (a->stages < 1) return 1;
   a->lo_ring_off = a->stages * a->stage_bytes;
   a->tile_off = a->lo_ring_off + (passes == 3 ? a->lo_stages * a->stage_bytes : 0);
-  a->bar_off = a->tile_off + 2 * kStepBytes;
+  a->bar_off = a->tile_off + a->n_bufs * kStepBytes;
   const char* dbg = getenv("PMT_TC_DEBUG");
   a->debug = dbg ? atoi(dbg) : 0;
   return 0;

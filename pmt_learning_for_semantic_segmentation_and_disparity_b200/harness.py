@@ -20,6 +20,100 @@ from .correlation import SpatialCorrelationSampler
 from .warp import apply_disparity
 
 
+class _PairedSyncBNFn(torch.autograd.Function):
+    """Batch norm of a concatenated [left; right] batch with the statistics of each half kept separate -- what two
+    consecutive calls of one nn.SyncBatchNorm on `left` and on `right` compute (the reference runs its siamese tower
+    twice, models/dsnet_t2.py:1159-1160) -- but with ONE collective per layer instead of two in the forward
+    (all_gather of both halves' mean / invstd / count) and one instead of two in the backward (all_reduce of both
+    halves' sum_dy / sum_dy_xmu).  SURVEY.md section 8 f4: the step's scaling is bound by the latency of these tiny
+    collectives, so halving their number is worth more than any bandwidth."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, running_mean, running_var, eps, momentum, group, world_size):
+        x = x.contiguous()
+        half = x.size(0) // 2
+        halves = (x[:half], x[half:])
+        C = x.size(1)
+        local = []
+        for xi in halves:
+            mean, invstd = torch.batch_norm_stats(xi, eps)
+            local += [mean, invstd]
+        count = torch.full((1,), halves[0].numel() // C, dtype=local[0].dtype, device=x.device)
+        if world_size > 1:
+            combined = torch.cat(local + [count])                                    # (4C + 1,)
+            gathered = torch.empty(world_size, combined.numel(), dtype=combined.dtype, device=x.device)
+            torch.distributed.all_gather_into_tensor(gathered, combined, group=group)
+            counts = gathered[:, 4 * C]
+        else:
+            gathered = torch.cat(local + [count]).unsqueeze(0)
+            counts = count
+        outs, saved = [], []
+        for i, xi in enumerate(halves):                                               # left first, like two calls
+            mean_all = gathered[:, 2 * i * C:(2 * i + 1) * C]
+            invstd_all = gathered[:, (2 * i + 1) * C:(2 * i + 2) * C]
+            mean, invstd = torch.batch_norm_gather_stats_with_counts(xi, mean_all, invstd_all, running_mean,
+                                                                     running_var, momentum, eps, counts.view(-1))
+            outs.append(torch.batch_norm_elemt(xi, weight, bias, mean, invstd, eps))
+            saved += [mean, invstd]
+        ctx.save_for_backward(x, weight, *saved, counts.to(torch.int32))
+        ctx.group, ctx.world_size = group, world_size
+        return torch.cat(outs)
+
+    @staticmethod
+    def backward(ctx, grad):
+        x, weight, mean_l, invstd_l, mean_r, invstd_r, counts = ctx.saved_tensors
+        grad = grad.contiguous()
+        half = x.size(0) // 2
+        C = x.size(1)
+        parts = ((x[:half], grad[:half], mean_l, invstd_l), (x[half:], grad[half:], mean_r, invstd_r))
+        red, gw, gb = [], None, None
+        for xi, gi, mean, invstd in parts:
+            sum_dy, sum_dy_xmu, gwi, gbi = torch.batch_norm_backward_reduce(gi, xi, mean, invstd, weight, True, True, True)
+            red += [sum_dy, sum_dy_xmu]
+            gw = gwi if gw is None else gw + gwi
+            gb = gbi if gb is None else gb + gbi
+        combined = torch.cat(red)                                                    # (4C,)
+        if ctx.world_size > 1:
+            torch.distributed.all_reduce(combined, group=ctx.group)
+        gins = []
+        for i, (xi, gi, mean, invstd) in enumerate(parts):
+            sum_dy = combined[2 * i * C:(2 * i + 1) * C]
+            sum_dy_xmu = combined[(2 * i + 1) * C:(2 * i + 2) * C]
+            gins.append(torch.batch_norm_backward_elemt(gi, xi, mean, invstd, weight, sum_dy, sum_dy_xmu, counts))
+        return torch.cat(gins), gw, gb, None, None, None, None, None, None
+
+
+class PairedSyncBatchNorm(nn.BatchNorm2d):
+    """Drop-in for the BatchNorm2d layers of a siamese tower that is fed [left; right] in one pass (see
+    _PairedSyncBNFn).  Single process: equals calling the BatchNorm2d on each half in turn."""
+
+    def forward(self, x):
+        if not self.training:
+            return F.batch_norm(x, self.running_mean, self.running_var, self.weight, self.bias, False, 0.0, self.eps)
+        if x.size(0) % 2:
+            raise ValueError("PairedSyncBatchNorm expects an even batch: [left; right]")
+        if self.num_batches_tracked is not None:
+            self.num_batches_tracked.add_(2)
+        dist = torch.distributed
+        ws = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
+        return _PairedSyncBNFn.apply(x, self.weight, self.bias, self.running_mean, self.running_var, self.eps,
+                                     self.momentum, None, ws)
+
+
+def pair_batchnorms(module: nn.Module) -> nn.Module:
+    """Replace every BatchNorm2d below `module` by a PairedSyncBatchNorm that shares its parameters and buffers."""
+    for name, child in module.named_children():
+        if isinstance(child, (nn.BatchNorm2d, nn.SyncBatchNorm)) and not isinstance(child, PairedSyncBatchNorm):
+            new = PairedSyncBatchNorm(child.num_features, child.eps, child.momentum, child.affine, child.track_running_stats)
+            new.weight, new.bias = child.weight, child.bias
+            new.running_mean, new.running_var, new.num_batches_tracked = (child.running_mean, child.running_var,
+                                                                          child.num_batches_tracked)
+            setattr(module, name, new)
+        else:
+            pair_batchnorms(child)
+    return module
+
+
 def _cbr(cin, cout, k=3, s=1):
     return nn.Sequential(nn.Conv2d(cin, cout, k, s, k // 2, bias=False), nn.BatchNorm2d(cout), nn.ReLU(inplace=True))
 
@@ -27,8 +121,10 @@ def _cbr(cin, cout, k=3, s=1):
 class SDNetLite(nn.Module):
     """Joint segmentation + disparity net with the reference's hot-path call pattern (1dcorr, max_disp 8 at 1/8)."""
 
-    def __init__(self, n_labels: int = 2, feat_ch: int = 352, max_disp: int = 8, backbone: str = "densenet121"):
+    def __init__(self, n_labels: int = 2, feat_ch: int = 352, max_disp: int = 8, backbone: str = "densenet121",
+                 paired_tower: bool = False):
         super().__init__()
+        self.paired_tower = paired_tower
         if backbone == "densenet121":
             import torchvision
 
@@ -39,6 +135,8 @@ class SDNetLite(nn.Module):
             self.tower = nn.Sequential(_cbr(3, 32, 3, 2), _cbr(32, 64, 3, 2), _cbr(64, 96, 3, 2))
             tower_ch = 96
         self.reduce = _cbr(tower_ch, feat_ch, 1)
+        if paired_tower:
+            self.pair_tower()
         self.patch = 2 * max_disp + 1                                   # patch_corr = (1, max_disp*2+1)
         self.correlation_sampler = SpatialCorrelationSampler(kernel_size=1, patch_size=(1, self.patch), stride=1,
                                                              padding=0, dilation_patch=1)
@@ -50,10 +148,21 @@ class SDNetLite(nn.Module):
         self.seg_r = nn.Sequential(_cbr(feat_ch, 64), nn.Conv2d(64, n_labels, 3, 1, 1))
         self.att = nn.Sequential(nn.Conv2d(1, 1, 3, 1, 1), nn.Sigmoid())
 
+    def pair_tower(self):
+        """Run the siamese tower once over [left; right] with per-half BN statistics and one collective per BN layer
+        (call again after nn.SyncBatchNorm.convert_sync_batchnorm, which replaces every _BatchNorm it finds)."""
+        self.paired_tower = True
+        pair_batchnorms(self.tower)
+        pair_batchnorms(self.reduce)
+        return self
+
     def forward(self, left, right):
         H, W = left.shape[-2:]
-        a = self.reduce(self.tower(left))
-        b = self.reduce(self.tower(right))
+        if self.paired_tower:
+            a, b = self.reduce(self.tower(torch.cat([left, right]))).chunk(2)
+        else:
+            a = self.reduce(self.tower(left))
+            b = self.reduce(self.tower(right))
         y = self.correlation_sampler(a, b)                              # (B,1,17,h,w)
         y = torch.squeeze(y, dim=1)                                     # 1dcorr: not divided by C
         y = self.corrConv2d(y)
@@ -82,7 +191,8 @@ def synthetic_batch(batch: int, h: int, w: int, n_labels: int, device, generator
 
 
 def build_training_step(world, batch_per_gpu: int = 4, h: int = 256, w: int = 512, n_labels: int = 2,
-                        backbone: str = "densenet121", sync_bn: bool = True, cuda_graph: bool = False):
+                        backbone: str = "densenet121", sync_bn: bool = True, cuda_graph: bool = False,
+                        paired_tower: bool = False):
     """Returns (step_fn, model): step_fn() runs one fwd + loss + bwd + Adam step on a fixed synthetic batch.
 
     cuda_graph=True captures the whole step -- forward, our hot-path kernels, backward, DDP's bucketed gradient
@@ -91,13 +201,15 @@ def build_training_step(world, batch_per_gpu: int = 4, h: int = 256, w: int = 51
     removes the host from the loop, which is what lets the step scale across GPUs."""
     dev = torch.device("cuda", world.local_rank)
     torch.manual_seed(1234)  # identical initial weights on every rank
-    model = SDNetLite(n_labels=n_labels, backbone=backbone).to(dev)
+    model = SDNetLite(n_labels=n_labels, backbone=backbone, paired_tower=paired_tower and sync_bn).to(dev)
     side = torch.cuda.Stream(device=dev)
     side.wait_stream(torch.cuda.current_stream(dev))
     with torch.cuda.stream(side):  # DDP must be built and warmed up on the stream family the graph is captured from
         if world.distributed:
             if sync_bn:
                 model = nn.SyncBatchNorm.convert_sync_batchnorm(model)
+                if paired_tower:
+                    model.pair_tower()
             model = nn.parallel.DistributedDataParallel(model, device_ids=[world.local_rank])
         opt = torch.optim.Adam(model.parameters(), lr=1.5e-3, eps=1e-7, capturable=cuda_graph)
         g = torch.Generator(device=dev).manual_seed(world.rank)
