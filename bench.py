@@ -35,8 +35,8 @@ UNIT = "pairs/s"
 N_SETS = 2  # rotating buffer sets (each 1.34 GB >> 126 MB L2)
 # dram__bytes_read.sum + dram__bytes_write.sum of one launch of the dominant kernel at this exact workload, from the
 # committed ncu --set full capture (per launch; the kernel reads g once per gradient, hence > algorithmic bytes)
-NCU_DRAM_BYTES_BWD = 671_543_552 + 245_852_928
-NCU_SOURCE = "profiles/r01_ncu_corr_tc_v6.md (ncu --set full, corr1d_bwd_tc_kernel<3>, B=4 headline workload)"
+NCU_DRAM_BYTES_BWD = 671_751_680 + 245_425_152
+NCU_SOURCE = "profiles/r01_ncu_corr_tc_v7.md (ncu --set full, corr1d_bwd_tc_kernel<3, 3>, B=4 headline workload)"
 
 
 def algorithmic_work(c=C, h=H, w=W, p=P):
@@ -314,7 +314,7 @@ def run_ours(args, world):
     tiles = (H * ((W + 127) // 128))
     tf_bwd = 2 * tiles * (128 * 64 * 320 * 2) * 3 * 1e-12      # TFLOP per pair, both gradients
     tf_fwd = tiles * (128 * 320 * 64 * 2) * 3 * 1e-12
-    roofline = {"bound": "hbm", "kernel": "corr1d_bwd_tc_kernel<3>", "achieved": bwd_gbs, "peak": hbm_peak, "unit": "GB/s",
+    roofline = {"bound": "hbm", "kernel": "corr1d_bwd_tc_kernel<3, 3>", "achieved": bwd_gbs, "peak": hbm_peak, "unit": "GB/s",
                 "frac": bwd_gbs / hbm_peak, "traffic": NCU_DRAM_BYTES_BWD, "traffic_source": NCU_SOURCE,
                 "peak_source": peak_src,
                 "ms_per_launch": ms_bwd, "algorithmic_bytes_per_launch": B * work["bytes_bwd"],
