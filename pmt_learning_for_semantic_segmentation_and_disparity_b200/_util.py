@@ -37,8 +37,15 @@ def same_device(*tensors):
     return dev
 
 
+_EMPTY = 256  # non-null, 16-byte aligned, never dereferenced: every entry point returns before touching a zero-sized buffer
+
+
 def ptr(t):
-    return ctypes.c_void_p(t.data_ptr()) if t is not None else ctypes.c_void_p(0)
+    """Device pointer of a tensor for the C ABI (NULL for None).  PyTorch gives empty tensors a NULL data pointer,
+    which the library would reject as a missing argument, so they are passed as a sentinel address instead."""
+    if t is None:
+        return ctypes.c_void_p(0)
+    return ctypes.c_void_p(t.data_ptr() if t.numel() else _EMPTY)
 
 
 def stream_ptr(device) -> ctypes.c_void_p:

@@ -28,6 +28,11 @@ constexpr int kLBlocks = kTM / 32;    // 4 boxes for the L tile
 constexpr int kMaxNB = 10;            // band boxes (P <= 193)
 constexpr int kRowsPerStep = 32;      // output planes per staging buffer / TMA store (= one TMEM column block)
 constexpr int kStepBytes = kRowsPerStep * kTM * 4;
+#ifndef PMT_FWD_XF_GROUPS
+#define PMT_FWD_XF_GROUPS 1
+#endif
+constexpr int kXfGroups = PMT_FWD_XF_GROUPS;   // groups of 4 transform warps (3xTF32); needs lo_stages >= kXfGroups
+constexpr int kFwdThreads3 = 32 * (6 + 4 * kXfGroups);
 
 struct TcFwdArgs {
   int C, H, W, P, rW, delta;
@@ -53,7 +58,7 @@ __device__ __forceinline__ uint64_t mn_desc(uint32_t saddr, uint32_t lbo, uint32
 }
 
 template <int kPasses>
-__global__ void __launch_bounds__(kPasses == 3 ? 320 : 192, 1)
+__global__ void __launch_bounds__(kPasses == 3 ? kFwdThreads3 : 192, 1)
 corr1d_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmL, const __grid_constant__ CUtensorMap tmR,
                      const __grid_constant__ CUtensorMap tmO, const TcFwdArgs a) {
   extern __shared__ __align__(1024) unsigned char smem[];
@@ -225,12 +230,17 @@ corr1d_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmL, const __grid_const
     if (wid == 2 && lane == 0) tc::tma_store_wait<0>();
   } else {
     // ===== transform warps (kPasses == 3): split staged fp32 into tf32 hi + lo =====
-    const int t = tid - 6 * 32;  // 0..127
+    // kXfGroups groups of 4 warps take the K chunks round-robin.  One group is the default: a second one was measured
+    // at the headline shape and changed nothing (166.6 vs 167.6 us) -- the split is not what the MMA warp waits for.
+    const int t = (tid - 6 * 32) & 127;      // 0..127 inside the group
+    const int xg = (tid - 6 * 32) >> 7;      // group
     const int nchunks = nboxes * (kBoxBytes / 16);
-    int st = 0, ls = 0;
-    uint32_t fph = 0, leph = 1;
+    int st = xg % a.stages, ls = xg % a.lo_stages;
+    uint32_t fph = (uint32_t)(xg / a.stages) & 1u, leph = ((uint32_t)(xg / a.lo_stages) & 1u) ^ 1u;
+    int g = 0;
     for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x) {
-      for (int k = 0; k < a.n_cchunks; ++k) {
+      for (int k = 0; k < a.n_cchunks; ++k, ++g) {
+        if (g % kXfGroups != xg) continue;
         mbar_wait(&full[st], fph);
         mbar_wait(&lo_empty[ls], leph);
         const unsigned char* sbase = smem + (size_t)st * a.stage_bytes;
@@ -258,8 +268,10 @@ corr1d_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmL, const __grid_const
         fence_proxy_async();  // make the rewritten stage visible to the tensor core's async-proxy reads
         __syncwarp();
         if (lane == 0) mbar_arrive(&xf_done[ls]);
-        if (++st == a.stages) st = 0, fph ^= 1u;
-        if (++ls == a.lo_stages) ls = 0, leph ^= 1u;
+        st += kXfGroups;
+        while (st >= a.stages) st -= a.stages, fph ^= 1u;
+        ls += kXfGroups;
+        while (ls >= a.lo_stages) ls -= a.lo_stages, leph ^= 1u;
       }
     }
   }
@@ -297,6 +309,7 @@ int fill_args(TcFwdArgs* a, int C, int H, int W, int P, int passes) {
   if (passes == 3) {
     a->lo_stages = total >= 6 ? 2 : 1;   // measured at the headline shape (7 stages): 5 raw + 2 lo beats 4 + 3
     if (const char* e = getenv("PMT_FWD_LO_STAGES")) a->lo_stages = atoi(e);
+    if (a->lo_stages < kXfGroups) return 1;
     a->stages = total - a->lo_stages;
   } else {
     a->lo_stages = 1;
@@ -341,7 +354,7 @@ int launch_corr1d_fwd_tc(const float* in1, const float* in2, float* out, int B, 
   const int64_t grid = tiles < sm_count() ? tiles : sm_count();  // persistent: one CTA per SM
   if (passes == 3) {
     PMT_CUDA_OK(cudaFuncSetAttribute(corr1d_fwd_tc_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
-    corr1d_fwd_tc_kernel<3><<<(unsigned)grid, 320, smem_bytes, st>>>(tmL, tmR, tmO, a);
+    corr1d_fwd_tc_kernel<3><<<(unsigned)grid, kFwdThreads3, smem_bytes, st>>>(tmL, tmR, tmO, a);
   } else {
     PMT_CUDA_OK(cudaFuncSetAttribute(corr1d_fwd_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
     corr1d_fwd_tc_kernel<1><<<(unsigned)grid, 192, smem_bytes, st>>>(tmL, tmR, tmO, a);
