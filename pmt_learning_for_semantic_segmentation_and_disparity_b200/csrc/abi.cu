@@ -6,6 +6,8 @@
 
 #include <mutex>
 
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace pmt {
@@ -49,6 +51,11 @@ void set_error(const char* fmt, ...) {
   va_end(ap);
 }
 const char* get_error() { return g_err; }
+
+int env_int_uncached(const char* name, int dflt) {
+  const char* e = getenv(name);
+  return e ? atoi(e) : dflt;
+}
 
 int sm_count() {
   static int cached[64] = {0};

@@ -51,6 +51,11 @@ inline int round_up(int a, int b) { return ceil_div(a, b) * b; }
 
 int sm_count();  // cached number of SMs of the current device
 
+// Tuning / ablation knobs read from the environment ONCE per process (getenv is a linear scan of environ; the launch
+// path of a 10-us kernel cannot afford several of them per call).  PMT_ENV_INT("NAME", default) caches per call site.
+int env_int_uncached(const char* name, int dflt);
+#define PMT_ENV_INT(name, dflt) ([]() -> int { static const int v = ::pmt::env_int_uncached(name, dflt); return v; }())
+
 // 4-D fp32 tensor map over a dense (B,C,H,W) tensor, box = (box_w, 1, box_c, 1), zero OOB fill.
 // Returns 0 on success (error text set otherwise).
 int make_tmap_nchw(CUtensorMap* map, const float* base, int B, int C, int H, int W, int box_w,

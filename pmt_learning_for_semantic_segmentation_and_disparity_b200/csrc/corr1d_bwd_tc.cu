@@ -588,7 +588,7 @@ int fill_args(TcBwdArgs* a, int C, int H, int W, int P, int passes, int groups) 
   a->a_base = 2 * a->acc_cols;
   int tmem_slots = (512 - a->a_base) / a->aslot_cols;
   if (tmem_slots > kMaxGdSlots) tmem_slots = kMaxGdSlots;
-  const bool want_tmem_a = getenv("PMT_NO_TMEM_A") == nullptr;
+  const bool want_tmem_a = PMT_ENV_INT("PMT_NO_TMEM_A", 0) == 0;
   int max_end = 0;
   for (int md = 0; md < 2; ++md) {
     TcBwdMode& m = a->m[md];
@@ -621,10 +621,8 @@ int fill_args(TcBwdArgs* a, int C, int H, int W, int P, int passes, int groups) 
   const int need_cols = a->m[0].tmem_a ? a->a_base + a->m[0].a_slots * a->aslot_cols : 2 * a->acc_cols;
   while (cols < need_cols) cols *= 2;
   a->tmem_cols = cols;
-  const char* dbg = getenv("PMT_TC_DEBUG");
-  a->debug = dbg ? atoi(dbg) : 0;
-  const char* rx = getenv("PMT_BWD_RELAX_NS");
-  a->relax_ns = rx ? atoi(rx) : 64;
+  a->debug = PMT_ENV_INT("PMT_TC_DEBUG", 0);
+  a->relax_ns = PMT_ENV_INT("PMT_BWD_RELAX_NS", 64);
   return 0;
 }
 
@@ -643,7 +641,7 @@ int launch_corr1d_bwd_tc(const float* in1, const float* in2, const float* gout, 
   TcBwdArgs a;
   PMT_CHECK_ARG(passes == 1 || passes == 3, "corr1d tc: passes must be 1 (tf32) or 3 (3xtf32)");
   int groups = passes == 3 ? 3 : 2;   // 3xTF32: 3 builder groups when their shared-memory rings fit, else 2
-  if (const char* e = getenv("PMT_BWD_GROUPS")) groups = atoi(e) == 2 ? 2 : 3;
+  if (const int e = PMT_ENV_INT("PMT_BWD_GROUPS", 0)) groups = e == 2 ? 2 : 3;
   if (fill_args(&a, C, H, W, P, passes, groups) != 0) groups = 2;
   PMT_CHECK_ARG(fill_args(&a, C, H, W, P, passes, groups) == 0, "corr1d tc bwd: unsupported shape C=%d P=%d", C, P);
   CUtensorMap tm1, tm2, tmG0, tmG1;
@@ -662,7 +660,7 @@ int launch_corr1d_bwd_tc(const float* in1, const float* in2, const float* gout, 
   if (n_cta < 2) n_cta = 2;
   // measured optimum at the headline shape: an even split with 3 builder groups, 72 of 148 with 2
   int n0 = (int)(n_cta * (a.m[0].tmem_a && groups == 2 && passes == 3 ? 0.4865 : 0.5) + 0.5);
-  if (const char* e = getenv("PMT_BWD_SPLIT")) n0 = atoi(e);  // tuning knob
+  if (const int e = PMT_ENV_INT("PMT_BWD_SPLIT", 0)) n0 = e;  // tuning knob
   if (n0 < 1) n0 = 1;
   if (n0 > n_cta - 1) n0 = (int)n_cta - 1;
   a.n_cta0 = n0;

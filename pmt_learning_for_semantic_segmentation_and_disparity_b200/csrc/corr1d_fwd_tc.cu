@@ -303,12 +303,12 @@ int fill_args(TcFwdArgs* a, int C, int H, int W, int P, int passes) {
   a->n_tiles = 0;  // set by the launcher (needs B)
   a->stage_bytes = (kLBlocks + a->NB) * kBoxBytes;
   a->n_bufs = 2;
-  if (const char* e = getenv("PMT_FWD_NBUF")) a->n_bufs = atoi(e) == 3 ? 3 : 2;
+  if (PMT_ENV_INT("PMT_FWD_NBUF", 2) == 3) a->n_bufs = 3;
   const int budget = 227 * 1024 - 1024 - a->n_bufs * kStepBytes;
   int total = budget / a->stage_bytes;  // ring stages that fit next to the two staging buffers
   if (passes == 3) {
     a->lo_stages = total >= 6 ? 2 : 1;   // measured at the headline shape (7 stages): 5 raw + 2 lo beats 4 + 3
-    if (const char* e = getenv("PMT_FWD_LO_STAGES")) a->lo_stages = atoi(e);
+    if (const int e = PMT_ENV_INT("PMT_FWD_LO_STAGES", 0)) a->lo_stages = e;
     if (a->lo_stages < kXfGroups) return 1;
     a->stages = total - a->lo_stages;
   } else {
@@ -320,8 +320,7 @@ int fill_args(TcFwdArgs* a, int C, int H, int W, int P, int passes) {
   a->lo_ring_off = a->stages * a->stage_bytes;
   a->tile_off = a->lo_ring_off + (passes == 3 ? a->lo_stages * a->stage_bytes : 0);
   a->bar_off = a->tile_off + a->n_bufs * kStepBytes;
-  const char* dbg = getenv("PMT_TC_DEBUG");
-  a->debug = dbg ? atoi(dbg) : 0;
+  a->debug = PMT_ENV_INT("PMT_TC_DEBUG", 0);
   return 0;
 }
 
