@@ -3,7 +3,7 @@
 #include <cuda_runtime.h>
 #include <stdio.h>
 #include <stdlib.h>
-#include "../pmt_learning_for_semantic_segmentation_and_disparity_b200/csrc/tc_common.cuh"
+#include "../../pmt_learning_for_semantic_segmentation_and_disparity_b200/csrc/tc_common.cuh"
 using namespace pmt;
 namespace pmt { void set_error(const char*, ...) {} const char* get_error() { return ""; } int sm_count() { return 148; } }
 

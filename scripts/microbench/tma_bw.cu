@@ -9,7 +9,7 @@
 #include <cuda_runtime.h>
 #include <stdio.h>
 #include <stdlib.h>
-#include "../pmt_learning_for_semantic_segmentation_and_disparity_b200/csrc/common.cuh"
+#include "../../pmt_learning_for_semantic_segmentation_and_disparity_b200/csrc/common.cuh"
 using namespace pmt;
 namespace pmt { void set_error(const char*, ...) {} const char* get_error() { return ""; } int sm_count() { return 148; } }
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,

@@ -1,6 +1,6 @@
 import ctypes, sys, os
 import torch
-sys.path.insert(0, "/root/repo")
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", ".."))
 import pmt_learning_for_semantic_segmentation_and_disparity_b200 as pmt
 lib = pmt.load_library(); dev = torch.device("cuda:0")
 vp = lambda t: ctypes.c_void_p(t.data_ptr())
