@@ -229,7 +229,11 @@ __global__ void __launch_bounds__(256) softargmin_fwd_kernel(const float* __rest
     float m[kV], s[kV], t[kV];
 #pragma unroll
     for (int v = 0; v < kV; ++v) m[v] = -INFINITY, s[v] = 0.f, t[v] = 0.f;
-    for (int d0 = 0; d0 < D; d0 += kDU) {
+    // blocks start at different planes and wrap (see dispreg_fwd_kernel): no lockstep walk over the planes
+    const int nb_ = (D + kDU - 1) / kDU;
+    const int boff_ = (int)(blockIdx.x % 4) * (nb_ / 4);
+    for (int t_ = 0; t_ < nb_; ++t_) {
+      const int d0 = ((t_ + boff_) % nb_) * kDU;
       float x[kDU][kV];
 #pragma unroll
       for (int j = 0; j < kDU; ++j) {
@@ -287,6 +291,8 @@ __global__ void __launch_bounds__(256) softargmin_bwd_kernel(const float* __rest
     for (int v = 0; v < kV; ++v) l[v] *= kLog2e;
     const float* cbase = cost + b * D * plane + k;
     float* gbase = gcost + b * D * plane + k;
+    // (walking the planes in a per-block staggered order, which helps the forward kernels, was measured SLOWER here:
+    // 147 vs 139 us -- this kernel also writes a plane per plane read)
     for (int d0 = 0; d0 < D; d0 += kDU) {
       float x[kDU][kV];
 #pragma unroll
@@ -321,7 +327,12 @@ __global__ void __launch_bounds__(256) dispreg_fwd_kernel(const float* __restric
     float acc[kV];
 #pragma unroll
     for (int v = 0; v < kV; ++v) acc[v] = 0.f;
-    for (int d0 = 0; d0 < D; d0 += kU) {
+    // blocks start at different planes (then wrap): threads of different blocks do not walk the planes in lockstep,
+    // which spreads the concurrent requests over more DRAM pages / L2 slices
+    const int nb = (D + kU - 1) / kU;
+    const int boff = (int)(blockIdx.x % 4) * (nb / 4);
+    for (int t = 0; t < nb; ++t) {
+      const int d0 = ((t + boff) % nb) * kU;
       float xv[kU][kV];
 #pragma unroll
       for (int j = 0; j < kU; ++j) {
