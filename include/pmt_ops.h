@@ -133,6 +133,31 @@ int pmt_warp1d_bwd_f32(const float* img, const float* off, const float* gout, fl
                        float* goff, int N, int C, int H, int W, int gout_cnhw, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * f4 (next row): SyncBatchNorm for a siamese pair fed as ONE batch x = [left; right] (2B,C,H,W).
+ * The reference runs its tower twice per step (models/dsnet_t2.py:1159-1160) under nn.SyncBatchNorm
+ * (torch_implementation.py:739): two invocations of every BN layer, each with its own batch statistics and its own
+ * collective.  These kernels keep the two halves' statistics separate (same semantics, running statistics updated for
+ * left then right) but let them travel in one all-gather / all-reduce per layer, which the caller (torch.distributed)
+ * performs between the two calls of each direction:
+ *   stats      : payload[(half*C+c)*2 + {0,1}] = mean, M2 = sum (x-mean)^2 of channel c in that half (local rank);
+ *                payload[4C] = B*HW (this rank's element count); payload has 4C+1 floats
+ *   apply      : gathered = [world][4C+1] (every rank's payload followed by its element count B*HW); combines them,
+ *                out = (x-mean)*invstd*weight + bias, saves mean[2][C], invstd[2][C] (+ total count at invstd[2C]),
+ *                updates running_mean/var (may be NULL) with momentum and the unbiased variance
+ *   bwd_reduce : sums[(half*C+c)*2 + {0,1}] = sum dy, sum dy*(x-mean); gw/gb (C, ZEROED by the caller) += local grads
+ *   bwd_apply  : sums after the cross-rank all-reduce; dx = (dy - sum_dy/N - (x-mean)*invstd^2*sum_dy_xmu/N)*invstd*weight
+ * HW = H*W.  weight/bias may be NULL (non-affine).
+ * ------------------------------------------------------------------------------------------- */
+int pmt_bn_pair_stats_f32(const float* x, float* payload, int B, int C, int HW, void* stream);
+int pmt_bn_pair_apply_f32(const float* x, const float* gathered, int world, const float* weight, const float* bias,
+                          float* running_mean, float* running_var, float momentum, float eps, float* out,
+                          float* save_mean, float* save_invstd, int B, int C, int HW, void* stream);
+int pmt_bn_pair_bwd_reduce_f32(const float* dy, const float* x, const float* save_mean, const float* save_invstd,
+                               float* sums, float* gw, float* gb, int B, int C, int HW, void* stream);
+int pmt_bn_pair_bwd_apply_f32(const float* dy, const float* x, const float* save_mean, const float* save_invstd,
+                              const float* weight, const float* sums, float* dx, int B, int C, int HW, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
  * Host-buffer entry point for the headline workload (what a non-PyTorch caller of the reference's
  * sampler backend would bind): forward + backward of the 1 x P correlation on HOST tensors.
  * Copies in (in1,in2,gout), runs both kernels, copies out (out,gin1,gin2), batch item by batch

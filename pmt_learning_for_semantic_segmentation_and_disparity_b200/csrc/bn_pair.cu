@@ -1,0 +1,252 @@
+// bn_pair.cu -- batch-norm kernels for a siamese pair fed as ONE batch [left; right].
+//
+// The reference runs its feature tower twice per step (models/dsnet_t2.py:1159-1160) under nn.SyncBatchNorm
+// (torch_implementation.py:739): every BN layer is invoked twice, each invocation with its own batch statistics and
+// its own cross-rank collective.  Here the tower runs once over x = (2B, C, H, W); the statistics of the two halves
+// stay separate (same semantics) but travel in ONE all-gather (forward) / ONE all-reduce (backward) per layer, and the
+// per-layer work is two kernels per direction instead of the ~9 ATen launches of the stock SyncBatchNorm path:
+//   bn_pair_stats      : per (half, channel) mean and M2 = sum (x-mean)^2       -> payload[2][C][2]  (+ count)
+//   bn_pair_apply      : combines the gathered payloads of all ranks (Chan's parallel variance), normalises,
+//                        applies the affine map, saves mean / invstd, updates the running statistics (left, then right)
+//   bn_pair_bwd_reduce : per (half, channel) sum_dy and sum_dy*(x-mean); grad_weight / grad_bias (local)
+//   bn_pair_bwd_apply  : dx = (dy - sum_dy/N - (x-mean) * invstd^2 * sum_dy_xmu/N) * invstd * w
+// All tensors are NCHW fp32, contiguous.  The collectives themselves stay in torch.distributed (NCCL).
+#include "common.cuh"
+
+namespace pmt {
+namespace {
+
+constexpr int kBnThreads = 256;
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// block-wide sum of two values; result valid in every thread
+__device__ __forceinline__ void block_sum2(float& a, float& b) {
+  __shared__ float sa[kBnThreads / 32], sb[kBnThreads / 32];
+  a = warp_sum(a);
+  b = warp_sum(b);
+  const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+  __syncthreads();   // protects the buffers against a previous call
+  if (l == 0) sa[w] = a, sb[w] = b;
+  __syncthreads();
+  a = l < kBnThreads / 32 ? sa[l] : 0.f;
+  b = l < kBnThreads / 32 ? sb[l] : 0.f;
+  a = warp_sum(a);
+  b = warp_sum(b);
+}
+
+// iterate the B*HW elements of channel c in one half: element e -> image b = e / HW, pixel e % HW
+template <typename F>
+__device__ __forceinline__ void for_channel(const float* __restrict__ x, int half, int c, int B, int C, int HW, F f) {
+  const bool vec = (HW & 3) == 0;
+  for (int b = 0; b < B; ++b) {
+    const float* row = x + ((int64_t)(half * B + b) * C + c) * HW;
+    if (vec) {
+      for (int i = threadIdx.x * 4; i < HW; i += kBnThreads * 4) {
+        const float4 v = __ldg(reinterpret_cast<const float4*>(row + i));
+        f(v.x, i), f(v.y, i + 1), f(v.z, i + 2), f(v.w, i + 3);
+      }
+    } else {
+      for (int i = threadIdx.x; i < HW; i += kBnThreads) f(__ldg(row + i), i);
+    }
+  }
+}
+
+// grid (C, 2).  Single pass with shifted sums (shift = first element of the channel): mean = K + S1/n,
+// M2 = S2 - S1^2/n -- as accurate as a two-pass algorithm unless the channel is constant to 7 digits.
+__global__ void __launch_bounds__(kBnThreads) bn_pair_stats_kernel(const float* __restrict__ x, float* __restrict__ payload,
+                                                                   int B, int C, int HW) {
+  const int c = blockIdx.x, half = blockIdx.y;
+  const float K = __ldg(x + ((int64_t)(half * B) * C + c) * HW);
+  float s1 = 0.f, s2 = 0.f;
+  for_channel(x, half, c, B, C, HW, [&](float v, int) {
+    const float d = v - K;
+    s1 += d;
+    s2 = fmaf(d, d, s2);
+  });
+  block_sum2(s1, s2);
+  if (threadIdx.x == 0) {
+    const float n = (float)B * (float)HW;
+    payload[(half * C + c) * 2 + 0] = K + s1 / n;
+    payload[(half * C + c) * 2 + 1] = fmaxf(s2 - s1 * s1 / n, 0.f);
+    if (c == 0 && half == 0) payload[4 * C] = n;   // this rank's element count per channel-half
+  }
+}
+
+// Chan et al.: combine (n_r, mean_r, M2_r) of `world` ranks.  gathered = [world][4C+1]: [half][c][2] then the count.
+__device__ __forceinline__ void combine(const float* __restrict__ gathered, int world, int stride, int half, int c, int C,
+                                        float& mean, float& var_biased, float& n_total) {
+  float N = 0.f, m = 0.f;
+  for (int r = 0; r < world; ++r) {
+    const float n = gathered[r * stride + 4 * C];
+    N += n;
+    m = fmaf(n, gathered[r * stride + (half * C + c) * 2], m);
+  }
+  m /= N;
+  float M2 = 0.f;
+  for (int r = 0; r < world; ++r) {
+    const float n = gathered[r * stride + 4 * C];
+    const float d = gathered[r * stride + (half * C + c) * 2] - m;
+    M2 += gathered[r * stride + (half * C + c) * 2 + 1] + n * d * d;
+  }
+  mean = m, var_biased = M2 / N, n_total = N;
+}
+
+// grid (2B*C): one block per (image, channel) row.
+__global__ void __launch_bounds__(kBnThreads) bn_pair_apply_kernel(const float* __restrict__ x, const float* __restrict__ gathered,
+                                                                   int world, const float* __restrict__ weight,
+                                                                   const float* __restrict__ bias, float* running_mean,
+                                                                   float* running_var, float momentum, float eps,
+                                                                   float* __restrict__ out, float* __restrict__ save_mean,
+                                                                   float* __restrict__ save_invstd, int B, int C, int HW) {
+  const int row = blockIdx.x, b = row / C, c = row % C, half = b >= B ? 1 : 0;
+  const int stride = 4 * C + 1;
+  __shared__ float s_scale, s_shift;
+  if (threadIdx.x == 0) {
+    float mean, var, N;
+    combine(gathered, world, stride, half, c, C, mean, var, N);
+    const float invstd = rsqrtf(var + eps);
+    const float w = weight ? weight[c] : 1.f, bb = bias ? bias[c] : 0.f;
+    s_scale = invstd * w;
+    s_shift = bb - mean * invstd * w;
+    if (b == half * B) {   // first image of the half: record the statistics once
+      save_mean[half * C + c] = mean;
+      save_invstd[half * C + c] = invstd;
+      if (row == 0) save_invstd[2 * C] = N;   // elements per channel-half over all ranks, for the backward
+    }
+    if (b == 0 && running_mean != nullptr) {
+      // what two consecutive BatchNorm calls do: left's update, then right's, unbiased variance
+      float rm = running_mean[c], rv = running_var[c];
+      rm = (1.f - momentum) * rm + momentum * mean;
+      rv = (1.f - momentum) * rv + momentum * var * (N / fmaxf(N - 1.f, 1.f));
+      float mean2, var2, N2;
+      combine(gathered, world, stride, 1, c, C, mean2, var2, N2);
+      rm = (1.f - momentum) * rm + momentum * mean2;
+      rv = (1.f - momentum) * rv + momentum * var2 * (N2 / fmaxf(N2 - 1.f, 1.f));
+      running_mean[c] = rm, running_var[c] = rv;
+    }
+  }
+  __syncthreads();
+  const float sc = s_scale, sh = s_shift;
+  const float* xr = x + (int64_t)row * HW;
+  float* o = out + (int64_t)row * HW;
+  if ((HW & 3) == 0) {
+    for (int i = threadIdx.x * 4; i < HW; i += kBnThreads * 4) {
+      const float4 v = __ldg(reinterpret_cast<const float4*>(xr + i));
+      *reinterpret_cast<float4*>(o + i) = make_float4(fmaf(v.x, sc, sh), fmaf(v.y, sc, sh), fmaf(v.z, sc, sh), fmaf(v.w, sc, sh));
+    }
+  } else {
+    for (int i = threadIdx.x; i < HW; i += kBnThreads) o[i] = fmaf(__ldg(xr + i), sc, sh);
+  }
+}
+
+// grid (C, 2): sums[(half*C+c)*2 + {0,1}] = sum_dy, sum_dy*(x-mean).  gw/gb (C) accumulate both halves: the half-0 block
+// writes, the half-1 block adds with an atomic (two addends: order-independent in fp32).
+__global__ void __launch_bounds__(kBnThreads) bn_pair_bwd_reduce_kernel(const float* __restrict__ dy, const float* __restrict__ x,
+                                                                        const float* __restrict__ save_mean,
+                                                                        const float* __restrict__ save_invstd,
+                                                                        float* __restrict__ sums, float* __restrict__ gw,
+                                                                        float* __restrict__ gb, int B, int C, int HW) {
+  const int c = blockIdx.x, half = blockIdx.y;
+  const float mean = save_mean[half * C + c];
+  float s1 = 0.f, s2 = 0.f;
+  const bool vec = (HW & 3) == 0;
+  for (int b = 0; b < B; ++b) {
+    const int64_t off = ((int64_t)(half * B + b) * C + c) * HW;
+    if (vec) {
+      for (int i = threadIdx.x * 4; i < HW; i += kBnThreads * 4) {
+        const float4 g = __ldg(reinterpret_cast<const float4*>(dy + off + i));
+        const float4 v = __ldg(reinterpret_cast<const float4*>(x + off + i));
+        s1 += (g.x + g.y) + (g.z + g.w);
+        s2 = fmaf(g.x, v.x - mean, s2), s2 = fmaf(g.y, v.y - mean, s2), s2 = fmaf(g.z, v.z - mean, s2),
+        s2 = fmaf(g.w, v.w - mean, s2);
+      }
+    } else {
+      for (int i = threadIdx.x; i < HW; i += kBnThreads) {
+        const float g = __ldg(dy + off + i);
+        s1 += g;
+        s2 = fmaf(g, __ldg(x + off + i) - mean, s2);
+      }
+    }
+  }
+  block_sum2(s1, s2);
+  if (threadIdx.x == 0) {
+    sums[(half * C + c) * 2 + 0] = s1;
+    sums[(half * C + c) * 2 + 1] = s2;
+    // gw/gb are zero-filled by the caller
+    atomicAdd(gw + c, s2 * save_invstd[half * C + c]);
+    atomicAdd(gb + c, s1);
+  }
+}
+
+// grid (2B*C).  sums are the all-reduced [2][C][2]; save_invstd[2C] = elements per channel-half over all ranks.
+__global__ void __launch_bounds__(kBnThreads) bn_pair_bwd_apply_kernel(const float* __restrict__ dy, const float* __restrict__ x,
+                                                                       const float* __restrict__ save_mean,
+                                                                       const float* __restrict__ save_invstd,
+                                                                       const float* __restrict__ weight,
+                                                                       const float* __restrict__ sums,
+                                                                       float* __restrict__ dx, int B, int C, int HW) {
+  const int row = blockIdx.x, b = row / C, c = row % C, half = b >= B ? 1 : 0;
+  const float mean = save_mean[half * C + c], invstd = save_invstd[half * C + c];
+  const float w = weight ? weight[c] : 1.f;
+  const float n_total = save_invstd[2 * C];
+  const float mean_dy = sums[(half * C + c) * 2] / n_total;
+  const float k = sums[(half * C + c) * 2 + 1] / n_total * invstd * invstd;
+  const float sc = invstd * w;
+  const float* g = dy + (int64_t)row * HW;
+  const float* xr = x + (int64_t)row * HW;
+  float* o = dx + (int64_t)row * HW;
+  if ((HW & 3) == 0) {
+    for (int i = threadIdx.x * 4; i < HW; i += kBnThreads * 4) {
+      const float4 gv = __ldg(reinterpret_cast<const float4*>(g + i));
+      const float4 v = __ldg(reinterpret_cast<const float4*>(xr + i));
+      *reinterpret_cast<float4*>(o + i) =
+          make_float4((gv.x - mean_dy - (v.x - mean) * k) * sc, (gv.y - mean_dy - (v.y - mean) * k) * sc,
+                      (gv.z - mean_dy - (v.z - mean) * k) * sc, (gv.w - mean_dy - (v.w - mean) * k) * sc);
+    }
+  } else {
+    for (int i = threadIdx.x; i < HW; i += kBnThreads) o[i] = (__ldg(g + i) - mean_dy - (__ldg(xr + i) - mean) * k) * sc;
+  }
+}
+
+}  // namespace
+
+int launch_bn_pair_stats(const float* x, float* payload, int B, int C, int HW, cudaStream_t st) {
+  if (B == 0 || C == 0 || HW == 0) return PMT_OK;
+  bn_pair_stats_kernel<<<dim3((unsigned)C, 2), kBnThreads, 0, st>>>(x, payload, B, C, HW);
+  PMT_LAUNCH_OK("bn_pair_stats_kernel");
+  return PMT_OK;
+}
+
+int launch_bn_pair_apply(const float* x, const float* gathered, int world, const float* weight, const float* bias,
+                         float* running_mean, float* running_var, float momentum, float eps, float* out, float* save_mean,
+                         float* save_invstd, int B, int C, int HW, cudaStream_t st) {
+  if (B == 0 || C == 0 || HW == 0) return PMT_OK;
+  bn_pair_apply_kernel<<<(unsigned)(2 * B * C), kBnThreads, 0, st>>>(x, gathered, world, weight, bias, running_mean, running_var,
+                                                                    momentum, eps, out, save_mean, save_invstd, B, C, HW);
+  PMT_LAUNCH_OK("bn_pair_apply_kernel");
+  return PMT_OK;
+}
+
+int launch_bn_pair_bwd_reduce(const float* dy, const float* x, const float* save_mean, const float* save_invstd, float* sums,
+                              float* gw, float* gb, int B, int C, int HW, cudaStream_t st) {
+  if (B == 0 || C == 0 || HW == 0) return PMT_OK;
+  bn_pair_bwd_reduce_kernel<<<dim3((unsigned)C, 2), kBnThreads, 0, st>>>(dy, x, save_mean, save_invstd, sums, gw, gb, B, C, HW);
+  PMT_LAUNCH_OK("bn_pair_bwd_reduce_kernel");
+  return PMT_OK;
+}
+
+int launch_bn_pair_bwd_apply(const float* dy, const float* x, const float* save_mean, const float* save_invstd,
+                             const float* weight, const float* sums, float* dx, int B, int C, int HW, cudaStream_t st) {
+  if (B == 0 || C == 0 || HW == 0) return PMT_OK;
+  bn_pair_bwd_apply_kernel<<<(unsigned)(2 * B * C), kBnThreads, 0, st>>>(dy, x, save_mean, save_invstd, weight, sums, dx, B, C,
+                                                                        HW);
+  PMT_LAUNCH_OK("bn_pair_bwd_apply_kernel");
+  return PMT_OK;
+}
+
+}  // namespace pmt

@@ -85,3 +85,31 @@ def test_paired_tower_model_level():
             losses.append(float(loss))
         assert abs(losses[0] - losses[1]) <= (1e-4 if it == 0 else 2e-3) * abs(losses[0]), (it, losses)
     assert int(par.tower[0][1].num_batches_tracked) == int(ref.tower[0][1].num_batches_tracked) == 12
+
+
+def test_paired_batchnorm_fused_kernels_match_aten_composition():
+    """csrc/bn_pair.cu (stats / apply / bwd_reduce / bwd_apply through the C ABI) against the ATen-op composition of the
+    same operator, fp32: outputs, input and parameter gradients, running statistics; odd H*W exercises the scalar path."""
+    from pmt_learning_for_semantic_segmentation_and_disparity_b200 import harness
+
+    DEV = torch.device("cuda:0")
+    for (B, C, H, W) in [(3, 8, 20, 28), (2, 5, 7, 9), (1, 32, 64, 128)]:
+        torch.manual_seed(C)
+        bn_f = harness.PairedSyncBatchNorm(C).to(DEV).train()
+        bn_a = harness.PairedSyncBatchNorm(C).to(DEV).train()
+        with torch.no_grad():
+            bn_f.weight.uniform_(0.5, 1.5), bn_f.bias.uniform_(-1, 1)
+        bn_a.load_state_dict(bn_f.state_dict())
+        bn_a.fused = False
+        x = (3.0 * torch.randn(2 * B, C, H, W, device=DEV) + 1.5)
+        xf, xa = x.clone().requires_grad_(True), x.clone().requires_grad_(True)
+        w = torch.randn_like(x)
+        of, oa = bn_f(xf), bn_a(xa)
+        assert float((of - oa).abs().max()) <= 2e-5 * float(oa.abs().max())
+        (of * w).sum().backward()
+        (oa * w).sum().backward()
+        for a, b, what in [(xf.grad, xa.grad, "dx"), (bn_f.weight.grad, bn_a.weight.grad, "gw"),
+                           (bn_f.bias.grad, bn_a.bias.grad, "gb"), (bn_f.running_mean, bn_a.running_mean, "rm"),
+                           (bn_f.running_var, bn_a.running_var, "rv")]:
+            err, scale = float((a - b).abs().max()), float(b.abs().max())
+            assert err <= 1e-4 * scale + 1e-6, f"{what} C={C}: {err:.3e} vs {scale:.3e}"
