@@ -10,6 +10,7 @@ from .correlation import (SpatialCorrelationSampler, SpatialCorrelationSamplerFu
 from .psmnet import (build_concat_volume, disparityregression, matchshifted, softargmin,  # noqa: F401
                      upsample_softargmin)
 from .warp import apply_disparity  # noqa: F401
+from .syncbn import PairedSyncBatchNorm, pair_batchnorms  # noqa: F401
 from .compat import install_reference_shims  # noqa: F401
 
 __version__ = "0.1.0"

@@ -1,0 +1,171 @@
+"""SyncBatchNorm for a siamese tower that is fed [left; right] in ONE pass.
+
+The reference runs its feature tower twice per step (models/dsnet_t2.py:1159-1160) under nn.SyncBatchNorm
+(torch_implementation.py:739): every BN layer is invoked twice, each time with its own batch statistics and its own
+collective.  `PairedSyncBatchNorm` keeps those semantics (per-half statistics, running statistics updated for left then
+right) but needs one collective and two kernel launches per layer and direction (csrc/bn_pair.cu through the C ABI).
+`pair_batchnorms(module)` converts the BatchNorm2d / SyncBatchNorm layers below a module; the caller then feeds
+`torch.cat([left, right])` and splits the result with `.chunk(2)`.
+"""
+from __future__ import annotations
+
+import torch
+import torch.nn.functional as F
+from torch import nn
+
+
+class _PairedSyncBNFn(torch.autograd.Function):
+    """Batch norm of a concatenated [left; right] batch with the statistics of each half kept separate -- what two
+    consecutive calls of one nn.SyncBatchNorm on `left` and on `right` compute (the reference runs its siamese tower
+    twice, models/dsnet_t2.py:1159-1160) -- but with ONE collective per layer instead of two in the forward
+    (all_gather of both halves' mean / invstd / count) and one instead of two in the backward (all_reduce of both
+    halves' sum_dy / sum_dy_xmu).  SURVEY.md section 8 f4: the step's scaling is bound by the latency of these tiny
+    collectives, so halving their number is worth more than any bandwidth."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, running_mean, running_var, eps, momentum, group, world_size):
+        x = x.contiguous()
+        half = x.size(0) // 2
+        halves = (x[:half], x[half:])
+        C = x.size(1)
+        local = []
+        for xi in halves:
+            mean, invstd = torch.batch_norm_stats(xi, eps)
+            local += [mean, invstd]
+        count = torch.full((1,), halves[0].numel() // C, dtype=local[0].dtype, device=x.device)
+        if world_size > 1:
+            combined = torch.cat(local + [count])                                    # (4C + 1,)
+            gathered = torch.empty(world_size, combined.numel(), dtype=combined.dtype, device=x.device)
+            torch.distributed.all_gather_into_tensor(gathered, combined, group=group)
+            counts = gathered[:, 4 * C]
+        else:
+            gathered = torch.cat(local + [count]).unsqueeze(0)
+            counts = count
+        outs, saved = [], []
+        for i, xi in enumerate(halves):                                               # left first, like two calls
+            mean_all = gathered[:, 2 * i * C:(2 * i + 1) * C]
+            invstd_all = gathered[:, (2 * i + 1) * C:(2 * i + 2) * C]
+            mean, invstd = torch.batch_norm_gather_stats_with_counts(xi, mean_all, invstd_all, running_mean,
+                                                                     running_var, momentum, eps, counts.view(-1))
+            outs.append(torch.batch_norm_elemt(xi, weight, bias, mean, invstd, eps))
+            saved += [mean, invstd]
+        ctx.save_for_backward(x, weight, *saved, counts.to(torch.int32))
+        ctx.group, ctx.world_size = group, world_size
+        return torch.cat(outs)
+
+    @staticmethod
+    def backward(ctx, grad):
+        x, weight, mean_l, invstd_l, mean_r, invstd_r, counts = ctx.saved_tensors
+        grad = grad.contiguous()
+        half = x.size(0) // 2
+        C = x.size(1)
+        parts = ((x[:half], grad[:half], mean_l, invstd_l), (x[half:], grad[half:], mean_r, invstd_r))
+        red, gw, gb = [], None, None
+        for xi, gi, mean, invstd in parts:
+            sum_dy, sum_dy_xmu, gwi, gbi = torch.batch_norm_backward_reduce(gi, xi, mean, invstd, weight, True, True, True)
+            red += [sum_dy, sum_dy_xmu]
+            gw = gwi if gw is None else gw + gwi
+            gb = gbi if gb is None else gb + gbi
+        combined = torch.cat(red)                                                    # (4C,)
+        if ctx.world_size > 1:
+            torch.distributed.all_reduce(combined, group=ctx.group)
+        gins = []
+        for i, (xi, gi, mean, invstd) in enumerate(parts):
+            sum_dy = combined[2 * i * C:(2 * i + 1) * C]
+            sum_dy_xmu = combined[(2 * i + 1) * C:(2 * i + 2) * C]
+            gins.append(torch.batch_norm_backward_elemt(gi, xi, mean, invstd, weight, sum_dy, sum_dy_xmu, counts))
+        return torch.cat(gins), gw, gb, None, None, None, None, None, None
+
+
+class _PairedSyncBNFusedFn(torch.autograd.Function):
+    """Same operator as _PairedSyncBNFn on this package's own kernels (csrc/bn_pair.cu, include/pmt_ops.h section f4):
+    two launches + one collective per direction instead of ~9 ATen launches + one collective.  fp32 CUDA NCHW only."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, running_mean, running_var, eps, momentum, group, world_size):
+        import ctypes
+
+        from . import _util as U
+
+        x = x.contiguous()
+        B2, C = x.size(0), x.size(1)
+        B, HW = B2 // 2, x[0, 0].numel()
+        dev = x.device
+        payload = torch.empty(4 * C + 1, device=dev, dtype=torch.float32)   # [half][c][mean, M2], count
+        U.call("pmt_bn_pair_stats_f32", dev, U.ptr(x), U.ptr(payload), B, C, HW)
+        if world_size > 1:
+            gathered = torch.empty(world_size, 4 * C + 1, device=dev, dtype=torch.float32)
+            torch.distributed.all_gather_into_tensor(gathered, payload, group=group)
+        else:
+            gathered = payload
+        out = torch.empty_like(x)
+        save_mean = torch.empty(2 * C, device=dev, dtype=torch.float32)
+        save_invstd = torch.empty(2 * C + 1, device=dev, dtype=torch.float32)   # [2C] = total count
+        lib = U._lib.load()
+        with torch.cuda.device(dev):
+            st = lib.pmt_bn_pair_apply_f32(U.ptr(x), U.ptr(gathered), int(world_size), U.ptr(weight), U.ptr(bias),
+                                           U.ptr(running_mean), U.ptr(running_var), ctypes.c_float(momentum),
+                                           ctypes.c_float(eps), U.ptr(out), U.ptr(save_mean), U.ptr(save_invstd), B, C, HW,
+                                           U.stream_ptr(dev))
+        U._lib.check(st, "pmt_bn_pair_apply_f32")
+        ctx.save_for_backward(x, weight, save_mean, save_invstd)
+        ctx.group, ctx.world_size = group, world_size
+        return out
+
+    @staticmethod
+    def backward(ctx, grad):
+        from . import _util as U
+
+        x, weight, save_mean, save_invstd = ctx.saved_tensors
+        grad = grad.contiguous()
+        B2, C = x.size(0), x.size(1)
+        B, HW = B2 // 2, x[0, 0].numel()
+        dev = x.device
+        sums = torch.empty(4 * C, device=dev, dtype=torch.float32)
+        gwb = torch.zeros(2, C, device=dev, dtype=torch.float32)
+        U.call("pmt_bn_pair_bwd_reduce_f32", dev, U.ptr(grad), U.ptr(x), U.ptr(save_mean), U.ptr(save_invstd), U.ptr(sums),
+               U.ptr(gwb[0]), U.ptr(gwb[1]), B, C, HW)
+        if ctx.world_size > 1:
+            torch.distributed.all_reduce(sums, group=ctx.group)
+        dx = torch.empty_like(x)
+        U.call("pmt_bn_pair_bwd_apply_f32", dev, U.ptr(grad), U.ptr(x), U.ptr(save_mean), U.ptr(save_invstd), U.ptr(weight),
+               U.ptr(sums), U.ptr(dx), B, C, HW)
+        gw = gwb[0] if weight is not None else None
+        gb = gwb[1] if weight is not None else None
+        return dx, gw, gb, None, None, None, None, None, None
+
+
+class PairedSyncBatchNorm(nn.BatchNorm2d):
+    """Drop-in for the BatchNorm2d layers of a siamese tower that is fed [left; right] in one pass (see
+    _PairedSyncBNFn).  Single process: equals calling the BatchNorm2d on each half in turn.  `fused` selects this
+    package's kernels (fp32 CUDA) over the composition of ATen ops (any dtype; the float64 reference of the tests)."""
+
+    fused = True
+
+    def forward(self, x):
+        if not self.training:
+            return F.batch_norm(x, self.running_mean, self.running_var, self.weight, self.bias, False, 0.0, self.eps)
+        if x.size(0) % 2:
+            raise ValueError("PairedSyncBatchNorm expects an even batch: [left; right]")
+        if self.num_batches_tracked is not None:
+            self.num_batches_tracked.add_(2)
+        dist = torch.distributed
+        ws = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
+        fused = (self.fused and x.is_cuda and x.dtype == torch.float32 and self.momentum is not None
+                 and x.data_ptr() % 16 == 0)
+        fn = _PairedSyncBNFusedFn if fused else _PairedSyncBNFn
+        return fn.apply(x, self.weight, self.bias, self.running_mean, self.running_var, self.eps, self.momentum, None, ws)
+
+
+def pair_batchnorms(module: nn.Module) -> nn.Module:
+    """Replace every BatchNorm2d below `module` by a PairedSyncBatchNorm that shares its parameters and buffers."""
+    for name, child in module.named_children():
+        if isinstance(child, (nn.BatchNorm2d, nn.SyncBatchNorm)) and not isinstance(child, PairedSyncBatchNorm):
+            new = PairedSyncBatchNorm(child.num_features, child.eps, child.momentum, child.affine, child.track_running_stats)
+            new.weight, new.bias = child.weight, child.bias
+            new.running_mean, new.running_var, new.num_batches_tracked = (child.running_mean, child.running_var,
+                                                                          child.num_batches_tracked)
+            setattr(module, name, new)
+        else:
+            pair_batchnorms(child)
+    return module
