@@ -146,16 +146,19 @@ int pmt_warp1d_bwd_f32(const float* img, const float* off, const float* gout, fl
  *                updates running_mean/var (may be NULL) with momentum and the unbiased variance
  *   bwd_reduce : sums[(half*C+c)*2 + {0,1}] = sum dy, sum dy*(x-mean); gw/gb (C, ZEROED by the caller) += local grads
  *   bwd_apply  : sums after the cross-rank all-reduce; dx = (dy - sum_dy/N - (x-mean)*invstd^2*sum_dy_xmu/N)*invstd*weight
- * HW = H*W.  weight/bias may be NULL (non-affine).
+ * HW = H*W.  weight/bias may be NULL (non-affine).  relu != 0 fuses the ReLU that follows every BN of the reference's
+ * towers (norm -> relu -> conv): apply clamps at 0, the backward kernels gate dy where the recomputed y was <= 0.
  * ------------------------------------------------------------------------------------------- */
 int pmt_bn_pair_stats_f32(const float* x, float* payload, int B, int C, int HW, void* stream);
 int pmt_bn_pair_apply_f32(const float* x, const float* gathered, int world, const float* weight, const float* bias,
                           float* running_mean, float* running_var, float momentum, float eps, float* out,
-                          float* save_mean, float* save_invstd, int B, int C, int HW, void* stream);
+                          float* save_mean, float* save_invstd, int B, int C, int HW, int relu, void* stream);
 int pmt_bn_pair_bwd_reduce_f32(const float* dy, const float* x, const float* save_mean, const float* save_invstd,
-                               float* sums, float* gw, float* gb, int B, int C, int HW, void* stream);
+                               float* sums, float* gw, float* gb, int B, int C, int HW, const float* weight,
+                               const float* bias, int relu, void* stream);
 int pmt_bn_pair_bwd_apply_f32(const float* dy, const float* x, const float* save_mean, const float* save_invstd,
-                              const float* weight, const float* sums, float* dx, int B, int C, int HW, void* stream);
+                              const float* weight, const float* sums, float* dx, int B, int C, int HW,
+                              const float* bias, int relu, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Host-buffer entry point for the headline workload (what a non-PyTorch caller of the reference's

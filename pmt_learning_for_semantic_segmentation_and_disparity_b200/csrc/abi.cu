@@ -37,11 +37,11 @@ int launch_upsample_softargmin_fwd(const float*, float*, float*, int, int, int, 
 int launch_dispreg_bwd(const float*, float*, int, int, int, int, cudaStream_t);
 int launch_bn_pair_stats(const float*, float*, int, int, int, cudaStream_t);
 int launch_bn_pair_apply(const float*, const float*, int, const float*, const float*, float*, float*, float, float, float*,
-                         float*, float*, int, int, int, cudaStream_t);
+                         float*, float*, int, int, int, int, cudaStream_t);
 int launch_bn_pair_bwd_reduce(const float*, const float*, const float*, const float*, float*, float*, float*, int, int, int,
-                              cudaStream_t);
+                              const float*, const float*, int, cudaStream_t);
 int launch_bn_pair_bwd_apply(const float*, const float*, const float*, const float*, const float*, const float*, float*, int,
-                             int, int, cudaStream_t);
+                             int, int, const float*, int, cudaStream_t);
 int launch_warp_fwd(const float*, const float*, float*, int, int, int, int, int, cudaStream_t);
 int launch_warp_bwd(const float*, const float*, const float*, float*, float*, int, int, int, int, int,
                     cudaStream_t);
@@ -331,26 +331,30 @@ int pmt_bn_pair_stats_f32(const float* x, float* payload, int B, int C, int HW, 
 
 int pmt_bn_pair_apply_f32(const float* x, const float* gathered, int world, const float* weight, const float* bias,
                           float* running_mean, float* running_var, float momentum, float eps, float* out,
-                          float* save_mean, float* save_invstd, int B, int C, int HW, void* stream) {
+                          float* save_mean, float* save_invstd, int B, int C, int HW, int relu, void* stream) {
   PMT_CHECK_ARG(x && gathered && out && save_mean && save_invstd, "bn_pair: null pointer");
   PMT_CHECK_ARG(B >= 0 && C >= 0 && HW >= 0 && world >= 1, "bn_pair: bad dimension");
   PMT_CHECK_ARG((running_mean == nullptr) == (running_var == nullptr), "bn_pair: running_mean/var must both be given or both NULL");
   return launch_bn_pair_apply(x, gathered, world, weight, bias, running_mean, running_var, momentum, eps, out, save_mean,
-                              save_invstd, B, C, HW, static_cast<cudaStream_t>(stream));
+                              save_invstd, B, C, HW, relu, static_cast<cudaStream_t>(stream));
 }
 
 int pmt_bn_pair_bwd_reduce_f32(const float* dy, const float* x, const float* save_mean, const float* save_invstd,
-                               float* sums, float* gw, float* gb, int B, int C, int HW, void* stream) {
+                               float* sums, float* gw, float* gb, int B, int C, int HW, const float* weight,
+                               const float* bias, int relu, void* stream) {
   PMT_CHECK_ARG(dy && x && save_mean && save_invstd && sums && gw && gb, "bn_pair: null pointer");
   PMT_CHECK_ARG(B >= 0 && C >= 0 && HW >= 0, "bn_pair: negative dimension");
-  return launch_bn_pair_bwd_reduce(dy, x, save_mean, save_invstd, sums, gw, gb, B, C, HW, static_cast<cudaStream_t>(stream));
+  return launch_bn_pair_bwd_reduce(dy, x, save_mean, save_invstd, sums, gw, gb, B, C, HW, weight, bias, relu,
+                                   static_cast<cudaStream_t>(stream));
 }
 
 int pmt_bn_pair_bwd_apply_f32(const float* dy, const float* x, const float* save_mean, const float* save_invstd,
-                              const float* weight, const float* sums, float* dx, int B, int C, int HW, void* stream) {
+                              const float* weight, const float* sums, float* dx, int B, int C, int HW,
+                              const float* bias, int relu, void* stream) {
   PMT_CHECK_ARG(dy && x && save_mean && save_invstd && sums && dx, "bn_pair: null pointer");
   PMT_CHECK_ARG(B >= 0 && C >= 0 && HW >= 0, "bn_pair: negative dimension");
-  return launch_bn_pair_bwd_apply(dy, x, save_mean, save_invstd, weight, sums, dx, B, C, HW, static_cast<cudaStream_t>(stream));
+  return launch_bn_pair_bwd_apply(dy, x, save_mean, save_invstd, weight, sums, dx, B, C, HW, bias, relu,
+                                  static_cast<cudaStream_t>(stream));
 }
 
 int pmt_warp1d_fwd_f32(const float* img, const float* off, float* out, int N, int C, int H, int W,

@@ -102,7 +102,8 @@ __global__ void __launch_bounds__(kBnThreads) bn_pair_apply_kernel(const float* 
                                                                    const float* __restrict__ bias, float* running_mean,
                                                                    float* running_var, float momentum, float eps,
                                                                    float* __restrict__ out, float* __restrict__ save_mean,
-                                                                   float* __restrict__ save_invstd, int B, int C, int HW) {
+                                                                   float* __restrict__ save_invstd, int B, int C, int HW,
+                                                                   int relu) {
   const int row = blockIdx.x, b = row / C, c = row % C, half = b >= B ? 1 : 0;
   const int stride = 4 * C + 1;
   __shared__ float s_scale, s_shift;
@@ -132,15 +133,17 @@ __global__ void __launch_bounds__(kBnThreads) bn_pair_apply_kernel(const float* 
   }
   __syncthreads();
   const float sc = s_scale, sh = s_shift;
+  const float lo = relu ? 0.f : -INFINITY;   // fused ReLU: y = max(bn(x), 0)
   const float* xr = x + (int64_t)row * HW;
   float* o = out + (int64_t)row * HW;
   if ((HW & 3) == 0) {
     for (int i = threadIdx.x * 4; i < HW; i += kBnThreads * 4) {
       const float4 v = __ldg(reinterpret_cast<const float4*>(xr + i));
-      *reinterpret_cast<float4*>(o + i) = make_float4(fmaf(v.x, sc, sh), fmaf(v.y, sc, sh), fmaf(v.z, sc, sh), fmaf(v.w, sc, sh));
+      *reinterpret_cast<float4*>(o + i) = make_float4(fmaxf(fmaf(v.x, sc, sh), lo), fmaxf(fmaf(v.y, sc, sh), lo),
+                                                      fmaxf(fmaf(v.z, sc, sh), lo), fmaxf(fmaf(v.w, sc, sh), lo));
     }
   } else {
-    for (int i = threadIdx.x; i < HW; i += kBnThreads) o[i] = fmaf(__ldg(xr + i), sc, sh);
+    for (int i = threadIdx.x; i < HW; i += kBnThreads) o[i] = fmaxf(fmaf(__ldg(xr + i), sc, sh), lo);
   }
 }
 
@@ -150,26 +153,34 @@ __global__ void __launch_bounds__(kBnThreads) bn_pair_bwd_reduce_kernel(const fl
                                                                         const float* __restrict__ save_mean,
                                                                         const float* __restrict__ save_invstd,
                                                                         float* __restrict__ sums, float* __restrict__ gw,
-                                                                        float* __restrict__ gb, int B, int C, int HW) {
+                                                                        float* __restrict__ gb, int B, int C, int HW,
+                                                                        const float* __restrict__ weight,
+                                                                        const float* __restrict__ bias, int relu) {
   const int c = blockIdx.x, half = blockIdx.y;
   const float mean = save_mean[half * C + c];
+  // fused ReLU: the incoming gradient only counts where y = (x-mean)*invstd*w + b was positive (y recomputed from x)
+  const float ysc = save_invstd[half * C + c] * (weight ? weight[c] : 1.f);
+  const float ysh = (bias ? bias[c] : 0.f) - mean * ysc;
+  auto gate = [&](float g, float v) { return (!relu || fmaf(v, ysc, ysh) > 0.f) ? g : 0.f; };
   float s1 = 0.f, s2 = 0.f;
   const bool vec = (HW & 3) == 0;
   for (int b = 0; b < B; ++b) {
     const int64_t off = ((int64_t)(half * B + b) * C + c) * HW;
     if (vec) {
       for (int i = threadIdx.x * 4; i < HW; i += kBnThreads * 4) {
-        const float4 g = __ldg(reinterpret_cast<const float4*>(dy + off + i));
+        float4 g = __ldg(reinterpret_cast<const float4*>(dy + off + i));
         const float4 v = __ldg(reinterpret_cast<const float4*>(x + off + i));
+        g.x = gate(g.x, v.x), g.y = gate(g.y, v.y), g.z = gate(g.z, v.z), g.w = gate(g.w, v.w);
         s1 += (g.x + g.y) + (g.z + g.w);
         s2 = fmaf(g.x, v.x - mean, s2), s2 = fmaf(g.y, v.y - mean, s2), s2 = fmaf(g.z, v.z - mean, s2),
         s2 = fmaf(g.w, v.w - mean, s2);
       }
     } else {
       for (int i = threadIdx.x; i < HW; i += kBnThreads) {
-        const float g = __ldg(dy + off + i);
+        const float v = __ldg(x + off + i);
+        const float g = gate(__ldg(dy + off + i), v);
         s1 += g;
-        s2 = fmaf(g, __ldg(x + off + i) - mean, s2);
+        s2 = fmaf(g, v - mean, s2);
       }
     }
   }
@@ -189,10 +200,13 @@ __global__ void __launch_bounds__(kBnThreads) bn_pair_bwd_apply_kernel(const flo
                                                                        const float* __restrict__ save_invstd,
                                                                        const float* __restrict__ weight,
                                                                        const float* __restrict__ sums,
-                                                                       float* __restrict__ dx, int B, int C, int HW) {
+                                                                       float* __restrict__ dx, int B, int C, int HW,
+                                                                       const float* __restrict__ bias, int relu) {
   const int row = blockIdx.x, b = row / C, c = row % C, half = b >= B ? 1 : 0;
   const float mean = save_mean[half * C + c], invstd = save_invstd[half * C + c];
   const float w = weight ? weight[c] : 1.f;
+  const float ysc = invstd * w, ysh = (bias ? bias[c] : 0.f) - mean * ysc;
+  auto gate = [&](float g, float v) { return (!relu || fmaf(v, ysc, ysh) > 0.f) ? g : 0.f; };
   const float n_total = save_invstd[2 * C];
   const float mean_dy = sums[(half * C + c) * 2] / n_total;
   const float k = sums[(half * C + c) * 2 + 1] / n_total * invstd * invstd;
@@ -202,14 +216,18 @@ __global__ void __launch_bounds__(kBnThreads) bn_pair_bwd_apply_kernel(const flo
   float* o = dx + (int64_t)row * HW;
   if ((HW & 3) == 0) {
     for (int i = threadIdx.x * 4; i < HW; i += kBnThreads * 4) {
-      const float4 gv = __ldg(reinterpret_cast<const float4*>(g + i));
+      float4 gv = __ldg(reinterpret_cast<const float4*>(g + i));
       const float4 v = __ldg(reinterpret_cast<const float4*>(xr + i));
+      gv.x = gate(gv.x, v.x), gv.y = gate(gv.y, v.y), gv.z = gate(gv.z, v.z), gv.w = gate(gv.w, v.w);
       *reinterpret_cast<float4*>(o + i) =
           make_float4((gv.x - mean_dy - (v.x - mean) * k) * sc, (gv.y - mean_dy - (v.y - mean) * k) * sc,
                       (gv.z - mean_dy - (v.z - mean) * k) * sc, (gv.w - mean_dy - (v.w - mean) * k) * sc);
     }
   } else {
-    for (int i = threadIdx.x; i < HW; i += kBnThreads) o[i] = (__ldg(g + i) - mean_dy - (__ldg(xr + i) - mean) * k) * sc;
+    for (int i = threadIdx.x; i < HW; i += kBnThreads) {
+      const float v = __ldg(xr + i);
+      o[i] = (gate(__ldg(g + i), v) - mean_dy - (v - mean) * k) * sc;
+    }
   }
 }
 
@@ -224,27 +242,30 @@ int launch_bn_pair_stats(const float* x, float* payload, int B, int C, int HW, c
 
 int launch_bn_pair_apply(const float* x, const float* gathered, int world, const float* weight, const float* bias,
                          float* running_mean, float* running_var, float momentum, float eps, float* out, float* save_mean,
-                         float* save_invstd, int B, int C, int HW, cudaStream_t st) {
+                         float* save_invstd, int B, int C, int HW, int relu, cudaStream_t st) {
   if (B == 0 || C == 0 || HW == 0) return PMT_OK;
   bn_pair_apply_kernel<<<(unsigned)(2 * B * C), kBnThreads, 0, st>>>(x, gathered, world, weight, bias, running_mean, running_var,
-                                                                    momentum, eps, out, save_mean, save_invstd, B, C, HW);
+                                                                    momentum, eps, out, save_mean, save_invstd, B, C, HW, relu);
   PMT_LAUNCH_OK("bn_pair_apply_kernel");
   return PMT_OK;
 }
 
 int launch_bn_pair_bwd_reduce(const float* dy, const float* x, const float* save_mean, const float* save_invstd, float* sums,
-                              float* gw, float* gb, int B, int C, int HW, cudaStream_t st) {
+                              float* gw, float* gb, int B, int C, int HW, const float* weight, const float* bias, int relu,
+                              cudaStream_t st) {
   if (B == 0 || C == 0 || HW == 0) return PMT_OK;
-  bn_pair_bwd_reduce_kernel<<<dim3((unsigned)C, 2), kBnThreads, 0, st>>>(dy, x, save_mean, save_invstd, sums, gw, gb, B, C, HW);
+  bn_pair_bwd_reduce_kernel<<<dim3((unsigned)C, 2), kBnThreads, 0, st>>>(dy, x, save_mean, save_invstd, sums, gw, gb, B, C, HW,
+                                                                         weight, bias, relu);
   PMT_LAUNCH_OK("bn_pair_bwd_reduce_kernel");
   return PMT_OK;
 }
 
 int launch_bn_pair_bwd_apply(const float* dy, const float* x, const float* save_mean, const float* save_invstd,
-                             const float* weight, const float* sums, float* dx, int B, int C, int HW, cudaStream_t st) {
+                             const float* weight, const float* sums, float* dx, int B, int C, int HW, const float* bias, int relu,
+                             cudaStream_t st) {
   if (B == 0 || C == 0 || HW == 0) return PMT_OK;
   bn_pair_bwd_apply_kernel<<<(unsigned)(2 * B * C), kBnThreads, 0, st>>>(dy, x, save_mean, save_invstd, weight, sums, dx, B, C,
-                                                                        HW);
+                                                                        HW, bias, relu);
   PMT_LAUNCH_OK("bn_pair_bwd_apply_kernel");
   return PMT_OK;
 }

@@ -56,8 +56,9 @@ class SDNetLite(nn.Module):
         self.att = nn.Sequential(nn.Conv2d(1, 1, 3, 1, 1), nn.Sigmoid())
 
     def pair_tower(self):
-        """Run the siamese tower once over [left; right] with per-half BN statistics and one collective per BN layer
-        (call again after nn.SyncBatchNorm.convert_sync_batchnorm, which replaces every _BatchNorm it finds)."""
+        """Run the siamese tower once over [left; right] with per-half BN statistics and one collective per BN layer.
+        Call it AFTER nn.SyncBatchNorm.convert_sync_batchnorm (which replaces every _BatchNorm it finds, paired ones
+        included, and would drop the ReLUs they have taken over), and only once."""
         self.paired_tower = True
         pair_batchnorms(self.tower)
         pair_batchnorms(self.reduce)
@@ -108,15 +109,18 @@ def build_training_step(world, batch_per_gpu: int = 4, h: int = 256, w: int = 51
     removes the host from the loop, which is what lets the step scale across GPUs."""
     dev = torch.device("cuda", world.local_rank)
     torch.manual_seed(1234)  # identical initial weights on every rank
-    model = SDNetLite(n_labels=n_labels, backbone=backbone, paired_tower=paired_tower and sync_bn).to(dev)
+    # the tower is paired AFTER the SyncBatchNorm conversion (which would otherwise replace the paired layers -- and
+    # lose the ReLUs they have taken over)
+    model = SDNetLite(n_labels=n_labels, backbone=backbone, paired_tower=False).to(dev)
     side = torch.cuda.Stream(device=dev)
     side.wait_stream(torch.cuda.current_stream(dev))
     with torch.cuda.stream(side):  # DDP must be built and warmed up on the stream family the graph is captured from
         if world.distributed:
             if sync_bn:
                 model = nn.SyncBatchNorm.convert_sync_batchnorm(model)
-                if paired_tower:
-                    model.pair_tower()
+        if paired_tower and sync_bn:
+            model.pair_tower()
+        if world.distributed:
             model = nn.parallel.DistributedDataParallel(model, device_ids=[world.local_rank])
         opt = torch.optim.Adam(model.parameters(), lr=1.5e-3, eps=1e-7, capturable=cuda_graph)
         g = torch.Generator(device=dev).manual_seed(world.rank)

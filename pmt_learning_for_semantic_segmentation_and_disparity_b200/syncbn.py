@@ -82,7 +82,7 @@ class _PairedSyncBNFusedFn(torch.autograd.Function):
     two launches + one collective per direction instead of ~9 ATen launches + one collective.  fp32 CUDA NCHW only."""
 
     @staticmethod
-    def forward(ctx, x, weight, bias, running_mean, running_var, eps, momentum, group, world_size):
+    def forward(ctx, x, weight, bias, running_mean, running_var, eps, momentum, group, world_size, relu=False):
         import ctypes
 
         from . import _util as U
@@ -106,17 +106,17 @@ class _PairedSyncBNFusedFn(torch.autograd.Function):
             st = lib.pmt_bn_pair_apply_f32(U.ptr(x), U.ptr(gathered), int(world_size), U.ptr(weight), U.ptr(bias),
                                            U.ptr(running_mean), U.ptr(running_var), ctypes.c_float(momentum),
                                            ctypes.c_float(eps), U.ptr(out), U.ptr(save_mean), U.ptr(save_invstd), B, C, HW,
-                                           U.stream_ptr(dev))
+                                           int(bool(relu)), U.stream_ptr(dev))
         U._lib.check(st, "pmt_bn_pair_apply_f32")
-        ctx.save_for_backward(x, weight, save_mean, save_invstd)
-        ctx.group, ctx.world_size = group, world_size
+        ctx.save_for_backward(x, weight, bias, save_mean, save_invstd)
+        ctx.group, ctx.world_size, ctx.relu = group, world_size, int(bool(relu))
         return out
 
     @staticmethod
     def backward(ctx, grad):
         from . import _util as U
 
-        x, weight, save_mean, save_invstd = ctx.saved_tensors
+        x, weight, bias, save_mean, save_invstd = ctx.saved_tensors
         grad = grad.contiguous()
         B2, C = x.size(0), x.size(1)
         B, HW = B2 // 2, x[0, 0].numel()
@@ -124,15 +124,15 @@ class _PairedSyncBNFusedFn(torch.autograd.Function):
         sums = torch.empty(4 * C, device=dev, dtype=torch.float32)
         gwb = torch.zeros(2, C, device=dev, dtype=torch.float32)
         U.call("pmt_bn_pair_bwd_reduce_f32", dev, U.ptr(grad), U.ptr(x), U.ptr(save_mean), U.ptr(save_invstd), U.ptr(sums),
-               U.ptr(gwb[0]), U.ptr(gwb[1]), B, C, HW)
+               U.ptr(gwb[0]), U.ptr(gwb[1]), B, C, HW, U.ptr(weight), U.ptr(bias), ctx.relu)
         if ctx.world_size > 1:
             torch.distributed.all_reduce(sums, group=ctx.group)
         dx = torch.empty_like(x)
         U.call("pmt_bn_pair_bwd_apply_f32", dev, U.ptr(grad), U.ptr(x), U.ptr(save_mean), U.ptr(save_invstd), U.ptr(weight),
-               U.ptr(sums), U.ptr(dx), B, C, HW)
+               U.ptr(sums), U.ptr(dx), B, C, HW, U.ptr(bias), ctx.relu)
         gw = gwb[0] if weight is not None else None
         gb = gwb[1] if weight is not None else None
-        return dx, gw, gb, None, None, None, None, None, None
+        return dx, gw, gb, None, None, None, None, None, None, None
 
 
 class PairedSyncBatchNorm(nn.BatchNorm2d):
@@ -141,10 +141,12 @@ class PairedSyncBatchNorm(nn.BatchNorm2d):
     package's kernels (fp32 CUDA) over the composition of ATen ops (any dtype; the float64 reference of the tests)."""
 
     fused = True
+    relu = False   # True: the ReLU that follows this BN is computed by the same kernels (pair_batchnorms sets it)
 
     def forward(self, x):
         if not self.training:
-            return F.batch_norm(x, self.running_mean, self.running_var, self.weight, self.bias, False, 0.0, self.eps)
+            y = F.batch_norm(x, self.running_mean, self.running_var, self.weight, self.bias, False, 0.0, self.eps)
+            return F.relu(y) if self.relu else y
         if x.size(0) % 2:
             raise ValueError("PairedSyncBatchNorm expects an even batch: [left; right]")
         if self.num_batches_tracked is not None:
@@ -153,19 +155,30 @@ class PairedSyncBatchNorm(nn.BatchNorm2d):
         ws = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
         fused = (self.fused and x.is_cuda and x.dtype == torch.float32 and self.momentum is not None
                  and x.data_ptr() % 16 == 0)
-        fn = _PairedSyncBNFusedFn if fused else _PairedSyncBNFn
-        return fn.apply(x, self.weight, self.bias, self.running_mean, self.running_var, self.eps, self.momentum, None, ws)
+        if fused:
+            return _PairedSyncBNFusedFn.apply(x, self.weight, self.bias, self.running_mean, self.running_var, self.eps,
+                                              self.momentum, None, ws, self.relu)
+        y = _PairedSyncBNFn.apply(x, self.weight, self.bias, self.running_mean, self.running_var, self.eps, self.momentum,
+                                  None, ws)
+        return F.relu(y) if self.relu else y
 
 
-def pair_batchnorms(module: nn.Module) -> nn.Module:
-    """Replace every BatchNorm2d below `module` by a PairedSyncBatchNorm that shares its parameters and buffers."""
-    for name, child in module.named_children():
+def pair_batchnorms(module: nn.Module, fuse_relu: bool = True) -> nn.Module:
+    """Replace every BatchNorm2d / SyncBatchNorm below `module` by a PairedSyncBatchNorm that shares its parameters and
+    buffers.  With fuse_relu, a BN whose NEXT sibling (registration order = call order in Sequential, torchvision's
+    _DenseLayer and _Transition) is an nn.ReLU takes the ReLU over (the sibling becomes nn.Identity)."""
+    names = [n for n, _ in module.named_children()]
+    for i, name in enumerate(names):
+        child = getattr(module, name)
         if isinstance(child, (nn.BatchNorm2d, nn.SyncBatchNorm)) and not isinstance(child, PairedSyncBatchNorm):
             new = PairedSyncBatchNorm(child.num_features, child.eps, child.momentum, child.affine, child.track_running_stats)
             new.weight, new.bias = child.weight, child.bias
             new.running_mean, new.running_var, new.num_batches_tracked = (child.running_mean, child.running_var,
                                                                           child.num_batches_tracked)
+            if fuse_relu and i + 1 < len(names) and isinstance(getattr(module, names[i + 1]), nn.ReLU):
+                new.relu = True
+                setattr(module, names[i + 1], nn.Identity())
             setattr(module, name, new)
         else:
-            pair_batchnorms(child)
+            pair_batchnorms(child, fuse_relu)
     return module

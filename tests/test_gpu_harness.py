@@ -46,6 +46,7 @@ def test_paired_batchnorm_equals_two_calls_fp64():
     par.load_state_dict(ref.state_dict())
     harness.pair_batchnorms(par)
     assert isinstance(par[1], harness.PairedSyncBatchNorm) and isinstance(par[4], harness.PairedSyncBatchNorm)
+    assert par[1].relu and isinstance(par[2], torch.nn.Identity) and not par[4].relu   # the ReLU moved into the BN
     left = torch.rand(3, 3, 20, 28, device=DEV, dtype=torch.float64)
     right = torch.rand(3, 3, 20, 28, device=DEV, dtype=torch.float64)
     w = torch.randn(6, 12, 10, 14, device=DEV, dtype=torch.float64)
@@ -93,10 +94,11 @@ def test_paired_batchnorm_fused_kernels_match_aten_composition():
     from pmt_learning_for_semantic_segmentation_and_disparity_b200 import harness
 
     DEV = torch.device("cuda:0")
-    for (B, C, H, W) in [(3, 8, 20, 28), (2, 5, 7, 9), (1, 32, 64, 128)]:
+    for (B, C, H, W, relu) in [(3, 8, 20, 28, False), (2, 5, 7, 9, True), (1, 32, 64, 128, True)]:
         torch.manual_seed(C)
         bn_f = harness.PairedSyncBatchNorm(C).to(DEV).train()
         bn_a = harness.PairedSyncBatchNorm(C).to(DEV).train()
+        bn_f.relu = bn_a.relu = relu          # fused ReLU in the kernels vs F.relu after the ATen composition
         with torch.no_grad():
             bn_f.weight.uniform_(0.5, 1.5), bn_f.bias.uniform_(-1, 1)
         bn_a.load_state_dict(bn_f.state_dict())
