@@ -6,12 +6,14 @@
 //   D[x (M=128 TMEM lanes)][c (N=C columns)] = sum over the band (K = 32*NKC columns, 320 for P=192).
 // Persistent CTAs (one per SM, half of them per gradient) walk tiles with every stage of the pipeline
 // running ahead across tile boundaries:
-//   * warps 0 and 14 (TMA producers): the feature band = B operand (rows c, K contiguous along w -> K-major), one
-//     128-byte-swizzled [C][32] box per K chunk into a deep ring; raw g into a second ring -- mode 0: the
+//   * warp 0 and the last warp (TMA producers): the feature band = B operand (rows c, K contiguous along w -> K-major),
+//     one 128-byte-swizzled [C][32] box per K chunk into a deep ring; raw g into a second ring -- mode 0: the
 //     tile's [P][128] slice as 32-row boxes (a box is recycled for the next tile as soon as its last
 //     chunk is built), mode 1: one [160][32] block per chunk (OOB rows/columns zero-filled by TMA);
-//   * warps 6-21 (16 builders): re-lay raw g out shared->shared into the swizzled K-major A operand Gd
-//     (bank-conflict-free LDS/STS); for 3xTF32 they write hi and lo copies and split the landed band;
+//   * warps 6.. (builders, groups of 4 warps that take the K chunks round-robin; 3 groups when three A slots fit,
+//     else 2): mode 0 writes the A operand Gd straight into TMEM (tcgen05.st: thread = Gd row, conflict-free column
+//     reads of the resident g slice), mode 1 re-lays raw g out shared->shared into the swizzled K-major A operand
+//     (all loads of a chunk before the first store); for 3xTF32 they write hi and lo copies and split the band;
 //   * warp 1 issues tcgen05.mma kind::tf32 (M=128, N=C, K=8; hi*hi + hi*lo + lo*hi for 3xTF32) into one
 //     of two TMEM accumulators and commits to the mbarriers that recycle the rings;
 //   * warps 2-5 (epilogue) drain the other accumulator with tcgen05.ld and store gin[c][x] directly:
