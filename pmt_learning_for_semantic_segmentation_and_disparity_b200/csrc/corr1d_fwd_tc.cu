@@ -7,9 +7,9 @@
 //     D[128 lanes][N cols] fp32 lives in TMEM;
 //   * warp 0 streams 16-channel slabs (boxes of 32 columns x 16 channels, 2 KB, 128-byte swizzle) of
 //     the L tile and the R band through a ring with TMA; warp 1 issues tcgen05.mma (M=128, N<=256,
-//     K=8 per instruction) and commits to mbarriers; 4 epilogue warps read TMEM with tcgen05.ld, un-skew
-//     D[w][j] -> out[p = j - w - delta][w] into a dense [P][128] staging tile (bank-conflict free: the
-//     row stride is 128 words) and ONE TMA store writes the whole tile;
+//     K=8 per instruction) and commits to mbarriers; 4 epilogue warps read TMEM with tcgen05.ld (every 32-column
+//     block exactly once), un-skew D[w][j] -> out[p = j - w - delta][w] into ping-pong [32][128] staging tiles
+//     (bank-conflict free: the row stride is 128 words) and issue one TMA store per 32 planes;
 //   * kPasses = 1: plain TF32 (10-bit mantissa inputs, fp32 accumulate) -- the reduced-precision variant;
 //     kPasses = 3: "3xTF32": 4 transform warps split every staged value into hi = tf32(x), lo = x - hi
 //     (exact in fp32) and the MMA warp accumulates hi*hi + hi*lo + lo*hi, recovering fp32-class
@@ -44,7 +44,7 @@ struct TcFwdArgs {
   int lo_stages;         // lo ring stages (3xTF32 only)
   int stage_bytes;       // (4+NB)*kBoxBytes
   int lo_ring_off;       // byte offset of the lo ring
-  int tile_off;          // byte offset of the two [48][128] staging buffers
+  int tile_off;          // byte offset of the [32][128] staging buffers
   int n_steps;           // epilogue steps of kRowsPerStep output planes
   int n_bufs;            // staging buffers (2 or 3)
   int bar_off;           // byte offset of the barriers
