@@ -115,3 +115,65 @@ def test_paired_batchnorm_fused_kernels_match_aten_composition():
                            (bn_f.running_var, bn_a.running_var, "rv")]:
             err, scale = float((a - b).abs().max()), float(b.abs().max())
             assert err <= 1e-4 * scale + 1e-6, f"{what} C={C}: {err:.3e} vs {scale:.3e}"
+
+
+def test_bn_pair_multi_rank_combine_on_one_gpu():
+    """The cross-rank path of the bn_pair kernels without a second GPU: two 'ranks' with different batches exchange
+    their stats payloads / backward sums by hand (what all_gather / all_reduce do), and every rank's result must equal
+    batch norm over the union of the two ranks' batches -- per half, as nn.SyncBatchNorm would compute it."""
+    import ctypes
+
+    from pmt_learning_for_semantic_segmentation_and_disparity_b200 import _util as U
+
+    DEV = torch.device("cuda:0")
+    torch.manual_seed(3)
+    B, C, H, W, world, eps, mom = 2, 6, 10, 12, 2, 1e-5, 0.1
+    HW = H * W
+    xs = [(2.0 * torch.randn(2 * B, C, H, W, device=DEV) + r) for r in range(world)]       # rank r: [left_r; right_r]
+    dys = [torch.randn(2 * B, C, H, W, device=DEV) for _ in range(world)]
+    weight, bias = torch.rand(C, device=DEV) + 0.5, torch.randn(C, device=DEV)
+    lib = U._lib.load()
+
+    # forward: stats on every rank, "all_gather", apply on every rank
+    gathered = torch.empty(world, 4 * C + 1, device=DEV)
+    for r in range(world):
+        U.call("pmt_bn_pair_stats_f32", DEV, U.ptr(xs[r]), U.ptr(gathered[r]), B, C, HW)
+    outs, saves = [], []
+    for r in range(world):
+        out, sm, si = torch.empty_like(xs[r]), torch.empty(2 * C, device=DEV), torch.empty(2 * C + 1, device=DEV)
+        rm, rv = torch.zeros(C, device=DEV), torch.ones(C, device=DEV)
+        st = lib.pmt_bn_pair_apply_f32(U.ptr(xs[r]), U.ptr(gathered), world, U.ptr(weight), U.ptr(bias), U.ptr(rm), U.ptr(rv),
+                                       ctypes.c_float(mom), ctypes.c_float(eps), U.ptr(out), U.ptr(sm), U.ptr(si), B, C, HW, 0,
+                                       U.stream_ptr(DEV))
+        assert st == 0
+        outs.append(out), saves.append((sm, si, rm, rv))
+    # reference: BatchNorm over the union of the ranks' batches, one call per half (float64)
+    ref_bn = torch.nn.BatchNorm2d(C, eps=eps, momentum=mom).to(DEV).double().train()
+    with torch.no_grad():
+        ref_bn.weight.copy_(weight), ref_bn.bias.copy_(bias)
+    halves = [torch.cat([x[:B] for x in xs]).double().requires_grad_(True), torch.cat([x[B:] for x in xs]).double().requires_grad_(True)]
+    refs = [ref_bn(h) for h in halves]                                  # left call, then right call
+    for r in range(world):
+        want = torch.cat([refs[0][r * B:(r + 1) * B], refs[1][r * B:(r + 1) * B]])
+        assert float((outs[r].double() - want).abs().max()) <= 2e-5 * float(want.abs().max())
+        assert float((saves[r][2].double() - ref_bn.running_mean).abs().max()) <= 1e-5
+        assert float((saves[r][3].double() - ref_bn.running_var).abs().max()) <= 1e-4
+    # backward: local reductions, "all_reduce", apply
+    loss = sum((refs[h][r * B:(r + 1) * B] * dys[r][h * B:(h + 1) * B].double()).sum() for h in range(2) for r in range(world))
+    loss.backward()
+    sums = [torch.empty(4 * C, device=DEV) for _ in range(world)]
+    gws = [torch.zeros(2, C, device=DEV) for _ in range(world)]
+    for r in range(world):
+        U.call("pmt_bn_pair_bwd_reduce_f32", DEV, U.ptr(dys[r]), U.ptr(xs[r]), U.ptr(saves[r][0]), U.ptr(saves[r][1]),
+               U.ptr(sums[r]), U.ptr(gws[r][0]), U.ptr(gws[r][1]), B, C, HW, U.ptr(weight), U.ptr(bias), 0)
+    total = sums[0] + sums[1]
+    for r in range(world):
+        dx = torch.empty_like(xs[r])
+        U.call("pmt_bn_pair_bwd_apply_f32", DEV, U.ptr(dys[r]), U.ptr(xs[r]), U.ptr(saves[r][0]), U.ptr(saves[r][1]),
+               U.ptr(weight), U.ptr(total), U.ptr(dx), B, C, HW, U.ptr(bias), 0)
+        want = torch.cat([halves[0].grad[r * B:(r + 1) * B], halves[1].grad[r * B:(r + 1) * B]])
+        assert float((dx.double() - want).abs().max()) <= 1e-4 * float(want.abs().max()) + 1e-7
+    # parameter gradients: the sum over ranks of the local ones (DDP's all-reduce)
+    gw, gb = gws[0][0] + gws[1][0], gws[0][1] + gws[1][1]
+    assert float((gw.double() - ref_bn.weight.grad).abs().max()) <= 1e-4 * float(ref_bn.weight.grad.abs().max())
+    assert float((gb.double() - ref_bn.bias.grad).abs().max()) <= 1e-4 * float(ref_bn.bias.grad.abs().max())
