@@ -128,12 +128,29 @@ def main():
     ms = timed(lambda i: lib.pmt_upsample_softargmin_fwd_f32(vp(low[i]), vp(out), None, B, D // 4, H // 4, W // 4, D, H, W, sp), 2)
     report("upsample_softargmin_fwd (fused f1)", "config3 logits (4,1,48,64,128) -> pred (4,256,512)", ms, lb + ob, B)
 
+    lse_u = torch.empty(B, H, W, device=dev)
+    lib.pmt_upsample_softargmin_fwd_f32(vp(low[0]), vp(out), vp(lse_u), B, D // 4, H // 4, W // 4, D, H, W, sp)
+    work = torch.empty(B, D // 4, H, W, device=dev)
+    glow = torch.empty_like(low[0])
+    ms = timed(lambda i: lib.pmt_upsample_softargmin_bwd_f32(vp(low[0]), vp(out), vp(lse_u), vp(go), vp(work), vp(glow), B, D // 4,
+                                                             H // 4, W // 4, D, H, W, sp), 1)
+    report("upsample_softargmin_bwd (fused f1)", "config3", ms, 2 * lb + 3 * ob, B)
+
     def unfused(i):
         up = torch.nn.functional.interpolate(low[i], size=[D, H, W], mode="trilinear", align_corners=False)[:, 0]
         return torch.sum(torch.softmax(up, dim=1) * ramp.repeat(B, 1, H, W), 1)
 
     ms = timed(unfused, 2)
     report("upsample+softmax+regression [ATen sequence of the reference]", "config3", ms, lb + ob, B)
+    lowg = low[0].clone().requires_grad_(True)
+
+    def unfused_fb(i):
+        lowg.grad = None
+        up = torch.nn.functional.interpolate(lowg, size=[D, H, W], mode="trilinear", align_corners=False)[:, 0]
+        torch.sum(torch.softmax(up, dim=1) * ramp.repeat(B, 1, H, W), 1).backward(go)
+
+    ms = timed(unfused_fb, 1)
+    report("upsample+softmax+regression fwd+bwd [ATen autograd]", "config3", ms, 2 * lb + 3 * ob, B)
     del c, gc
 
     # ---- warp (config 4: 540x960, C=3; production 256x512 C=2) --------------------------------------

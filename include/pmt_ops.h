@@ -111,10 +111,18 @@ int pmt_softargmin_bwd_f32(const float* cost, const float* out, const float* lse
 /* f1 (next row): F.upsample(cost3, [D,H,W], mode='trilinear') fused into the soft-argmin --
  * models_psmnet/stackhourglass.py:149-155 (and :138-147 for pred1/pred2).  `lowres` is (B,Dq,Hq,Wq) (the squeezed
  * (B,1,Dq,Hq,Wq) logits); the (B,D,H,W) upsampled volume is never materialised.  align_corners=False semantics of
- * ATen (scale = in/out, src = scale*(dst+0.5)-0.5 clamped at 0).  `lse` (B,H,W) may be NULL.  Forward only: the
- * training path materialises the volume and uses pmt_softargmin_bwd_f32. */
+ * ATen (scale = in/out, src = scale*(dst+0.5)-0.5 clamped at 0).  `lse` (B,H,W) may be NULL in the forward.
+ * Backward: glowres = d(sum gout*out)/d lowres without the volume either: a first kernel writes, per output pixel,
+ * the gradient w.r.t. the Dq bilinearly sampled source planes into `workspace` (B*Dq*H*W floats, caller-allocated),
+ * a second one applies the adjoint of the spatial interpolation (deterministic gather).  `out` and `lse` are the
+ * forward's results.  pmt_upsample_softargmin_bwd_supported() = 1 when the shape fits the fused kernels (shared-memory
+ * footprint, interpolation windows <= 40); otherwise the caller must differentiate the unfused sequence. */
 int pmt_upsample_softargmin_fwd_f32(const float* lowres, float* out, float* lse, int B, int Dq, int Hq,
                                     int Wq, int D, int H, int W, void* stream);
+int pmt_upsample_softargmin_bwd_supported(int B, int Dq, int Hq, int Wq, int D, int H, int W);
+int pmt_upsample_softargmin_bwd_f32(const float* lowres, const float* out, const float* lse, const float* gout,
+                                    float* workspace, float* glowres, int B, int Dq, int Hq, int Wq, int D, int H,
+                                    int W, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * a4. apply_disparity(input_images, x_offset, wrap_mode='edge') -- models/torch_dsnet.py:10-86.

@@ -36,6 +36,8 @@ _SIGNATURES = {
     "pmt_softargmin_fwd_f32": [_P, _P, _P, _I, _I, _I, _I, _P],
     "pmt_softargmin_bwd_f32": [_P, _P, _P, _P, _P, _I, _I, _I, _I, _P],
     "pmt_upsample_softargmin_fwd_f32": [_P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P],
+    "pmt_upsample_softargmin_bwd_supported": [_I, _I, _I, _I, _I, _I, _I],
+    "pmt_upsample_softargmin_bwd_f32": [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P],
     "pmt_bn_pair_stats_f32": [_P, _P, _I, _I, _I, _P],
     "pmt_bn_pair_apply_f32": [_P, _P, _I, _P, _P, _P, _P, _F, _F, _P, _P, _P, _I, _I, _I, _I, _P],
     "pmt_bn_pair_bwd_reduce_f32": [_P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _P, _P, _I, _P],

@@ -34,6 +34,9 @@ int launch_softargmin_bwd(const float*, const float*, const float*, const float*
                           int, int, cudaStream_t);
 int launch_dispreg_fwd(const float*, float*, int, int, int, int, cudaStream_t);
 int launch_upsample_softargmin_fwd(const float*, float*, float*, int, int, int, int, int, int, int, cudaStream_t);
+int launch_upsample_softargmin_bwd(const float*, const float*, const float*, const float*, float*, float*, int, int, int, int,
+                                   int, int, int, cudaStream_t);
+int upsample_softargmin_bwd_supported(int, int, int, int, int, int, int);
 int launch_dispreg_bwd(const float*, float*, int, int, int, int, cudaStream_t);
 int launch_bn_pair_stats(const float*, float*, int, int, int, cudaStream_t);
 int launch_bn_pair_apply(const float*, const float*, int, const float*, const float*, float*, float*, float, float, float*,
@@ -355,6 +358,19 @@ int pmt_bn_pair_bwd_apply_f32(const float* dy, const float* x, const float* save
   PMT_CHECK_ARG(B >= 0 && C >= 0 && HW >= 0, "bn_pair: negative dimension");
   return launch_bn_pair_bwd_apply(dy, x, save_mean, save_invstd, weight, sums, dx, B, C, HW, bias, relu,
                                   static_cast<cudaStream_t>(stream));
+}
+
+int pmt_upsample_softargmin_bwd_supported(int B, int Dq, int Hq, int Wq, int D, int H, int W) {
+  return upsample_softargmin_bwd_supported(B, Dq, Hq, Wq, D, H, W);
+}
+
+int pmt_upsample_softargmin_bwd_f32(const float* lowres, const float* out, const float* lse, const float* gout,
+                                    float* workspace, float* glowres, int B, int Dq, int Hq, int Wq, int D, int H, int W,
+                                    void* stream) {
+  PMT_CHECK_ARG(lowres && out && lse && gout && workspace && glowres, "upsample_softargmin backward: null pointer");
+  PMT_CHECK_ARG(B >= 0 && Dq >= 1 && Hq >= 1 && Wq >= 1 && D >= 1 && H >= 1 && W >= 1, "upsample_softargmin: bad dimension");
+  return launch_upsample_softargmin_bwd(lowres, out, lse, gout, workspace, glowres, B, Dq, Hq, Wq, D, H, W,
+                                        static_cast<cudaStream_t>(stream));
 }
 
 int pmt_warp1d_fwd_f32(const float* img, const float* off, float* out, int N, int C, int H, int W,

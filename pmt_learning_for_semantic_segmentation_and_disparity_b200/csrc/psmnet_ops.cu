@@ -480,10 +480,17 @@ __global__ void __launch_bounds__(256) upsample_softargmin_fwd_kernel(const floa
 // broadcast: 4 neighbouring pixels share their taps) instead of scattered global loads.  Same arithmetic, same order.
 constexpr int kUpTH = 4, kUpTW = 64;
 
+// kBwd = false: forward (writes out, lse).  kBwd = true: first half of the backward -- out / lse are INPUTS, and with
+// g_x[d] = gout * p_d * (d - out) the kernel writes U[b,q,h,w] = sum_d g_x[d] * Wd(d -> q), the gradient w.r.t. the
+// bilinearly sampled source planes (Wd = the disparity-axis interpolation weights); upsample_adjoint2d_kernel then
+// applies the transposed spatial interpolation.
+template <bool kBwd>
 __global__ void __launch_bounds__(kUpTH * kUpTW) upsample_softargmin_tiled_kernel(const float* __restrict__ lowres,
                                                                                    float* __restrict__ out,
                                                                                    float* __restrict__ lse, UpArgs a,
-                                                                                   int fr_max, int fc_max) {
+                                                                                   int fr_max, int fc_max,
+                                                                                   const float* __restrict__ gout,
+                                                                                   float* __restrict__ U) {
   extern __shared__ float up_smem[];
   int* tab_beg = reinterpret_cast<int*>(up_smem);   // [Dq+1]: first output plane whose lower source plane is >= q
   float* tab_l1 = up_smem + a.Dq + 1;                // [D]: weight of the upper source plane
@@ -532,6 +539,31 @@ __global__ void __launch_bounds__(kUpTH * kUpTW) upsample_softargmin_tiled_kerne
     const float* p = p00 + q * per_plane;
     return kLog2e * (hl0 * (wl0 * p[0] + wl1 * p[d01]) + hl1 * (wl0 * p[d10] + wl1 * p[d10 + d01]));
   };
+  const int64_t idx = ((int64_t)b * a.H + h) * a.W + w;
+  if (kBwd) {
+    const float g = __ldg(gout + idx), o = out[idx], l2 = lse[idx] * kLog2e;
+    float* up = U + ((int64_t)b * a.Dq * a.H + h) * (int64_t)a.W + w;
+    const int64_t ustride = (int64_t)a.H * a.W;
+    float s_cur = plane(0), carry = 0.f;
+    float df = (float)tab_beg[0];
+    for (int q = 0; q < a.Dq; ++q) {
+      const float s_nxt = plane(q + 1 < a.Dq ? q + 1 : q);
+      const int dend = tab_beg[q + 1];
+      const float c = s_cur - l2, diff = s_nxt - s_cur;
+      float a0 = 0.f, a1 = 0.f;
+      for (int d = tab_beg[q]; d < dend; ++d) {
+        const float l1 = tab_l1[d];
+        const float gx = g * fast_exp2(fmaf(l1, diff, c)) * (df - o);   // gout * p_d * (d - pred)
+        a1 = fmaf(gx, l1, a1);
+        a0 += gx - gx * l1;
+        df += 1.f;
+      }
+      up[q * ustride] = carry + a0;   // plane q: lower tap of its own group + upper tap of the previous group
+      carry = a1;
+      s_cur = s_nxt;
+    }
+    return;
+  }
   // Output planes d in [beg[q], beg[q+1]) blend source planes q and q+1: x_d = s_q + l1_d * (s_{q+1} - s_q), a convex
   // combination, so max(s_q, s_{q+1}) bounds every x_d of the group: the running maximum is updated once per source
   // plane (one rescale) instead of once per output plane.
@@ -556,9 +588,54 @@ __global__ void __launch_bounds__(kUpTH * kUpTW) upsample_softargmin_tiled_kerne
     }
     s_cur = s_nxt;
   }
-  const int64_t idx = ((int64_t)b * a.H + h) * a.W + w;
   out[idx] = t / s;
   if (lse != nullptr) lse[idx] = (m + log2f(s)) * kLn2;
+}
+
+// Second half of the backward: glow[b,q,hq,wq] = sum_{h,w} U[b,q,h,w] * Wh(h -> hq) * Ww(w -> wq), the adjoint of the
+// bilinear (align_corners=False) up-sampling of one plane.  One thread per low-res element gathers from the window of
+// output rows / columns whose two taps include it (deterministic, no atomics).
+constexpr int kAdjMaxWin = 40;
+__device__ __forceinline__ int adjoint_window(float scale, int q, int in_size, int out_size, float* wgt, int& lo) {
+  // outputs o with src(o) in (q-1, q+1): o in ((q-0.5)/scale - 0.5, (q+1.5)/scale - 0.5); one more on each side for rounding
+  int o_lo = (int)floorf(((float)q - 0.5f) / scale - 0.5f) - 1;
+  int o_hi = (int)ceilf(((float)q + 1.5f) / scale - 0.5f) + 1;
+  o_lo = o_lo < 0 ? 0 : o_lo;
+  o_hi = o_hi > out_size - 1 ? out_size - 1 : o_hi;
+  lo = o_lo;
+  int n = o_hi - o_lo + 1;
+  n = n > kAdjMaxWin ? kAdjMaxWin : n;   // the launcher guarantees the window fits
+  for (int i = 0; i < n; ++i) {
+    int i0, i1;
+    float l0, l1;
+    src_index(scale, o_lo + i, in_size, i0, i1, l0, l1);
+    wgt[i] = (i0 == q ? l0 : 0.f) + (i1 == q ? l1 : 0.f);
+  }
+  return n;
+}
+
+__global__ void __launch_bounds__(256) upsample_adjoint2d_kernel(const float* __restrict__ U, float* __restrict__ glow,
+                                                                 UpArgs a, int64_t total) {
+  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (int64_t)gridDim.x * blockDim.x) {
+    const int wq = (int)(idx % a.Wq);
+    const int hq = (int)((idx / a.Wq) % a.Hq);
+    const int64_t bq = idx / ((int64_t)a.Wq * a.Hq);   // b * Dq + q
+    float wh[kAdjMaxWin], ww[kAdjMaxWin];
+    int h_lo, w_lo;
+    const int nh = adjoint_window(a.sh, hq, a.Hq, a.H, wh, h_lo);
+    const int nw = adjoint_window(a.sw, wq, a.Wq, a.W, ww, w_lo);
+    const float* up = U + bq * a.H * (int64_t)a.W;
+    float acc = 0.f;
+    for (int i = 0; i < nh; ++i) {
+      if (wh[i] == 0.f) continue;
+      const float* row = up + (int64_t)(h_lo + i) * a.W + w_lo;
+      float r = 0.f;
+      for (int j = 0; j < nw; ++j) r = fmaf(ww[j], __ldg(row + j), r);
+      acc = fmaf(wh[i], r, acc);
+    }
+    glow[idx] = acc;
+  }
 }
 
 int stream_grid(int64_t nthreads, int block = 256) {
@@ -636,28 +713,67 @@ int launch_softargmin_bwd(const float* cost, const float* out, const float* lse,
   return PMT_OK;
 }
 
+// footprint / shared-memory plan of the tiled kernels; false if the shape needs the gather kernel instead
+static bool upsample_tiled_plan(const UpArgs& a, int* fr_max, int* fc_max, size_t* bytes) {
+  // footprint bound of a kUpTH x kUpTW output block: (block-1)*scale + 2 source rows/columns, +1 for rounding
+  *fr_max = (int)((kUpTH - 1) * a.sh) + 3 < a.Hq ? (int)((kUpTH - 1) * a.sh) + 3 : a.Hq;
+  *fc_max = (int)((kUpTW - 1) * a.sw) + 3 < a.Wq ? (int)((kUpTW - 1) * a.sw) + 3 : a.Wq;
+  *bytes = (size_t)(a.Dq + 1 + a.D) * 4 + (size_t)a.Dq * *fr_max * *fc_max * 4;
+  return *bytes <= 64 * 1024 && ceil_div64(a.H, kUpTH) <= 65535 && a.B <= 65535;
+}
+
 int launch_upsample_softargmin_fwd(const float* lowres, float* out, float* lse, int B, int Dq, int Hq, int Wq, int D,
                                    int H, int W, cudaStream_t st) {
   const int64_t total = (int64_t)B * H * W;
   if (total == 0) return PMT_OK;
   UpArgs a{B, Dq, Hq, Wq, D, H, W, (float)Dq / (float)D, (float)Hq / (float)H, (float)Wq / (float)W};
   PMT_CHECK_ARG(D <= 4096, "upsample_softargmin: maxdisp %d too large for the weight table", D);
-  // footprint bound of a kUpTH x kUpTW output block: (block-1)*scale + 2 source rows/columns, +1 for rounding
-  const int fr_max = (int)((kUpTH - 1) * a.sh) + 3 < Hq ? (int)((kUpTH - 1) * a.sh) + 3 : Hq;
-  const int fc_max = (int)((kUpTW - 1) * a.sw) + 3 < Wq ? (int)((kUpTW - 1) * a.sw) + 3 : Wq;
-  const size_t tile_bytes = (size_t)(Dq + 1 + D) * 4 + (size_t)Dq * fr_max * fc_max * 4;
+  int fr_max, fc_max;
+  size_t tile_bytes;
   const int64_t gy = ceil_div64(H, kUpTH), gx = ceil_div64(W, kUpTW);
   static const bool force_gather = getenv("PMT_UPSOFT_GATHER") != nullptr;
-  if (tile_bytes <= 64 * 1024 && gy <= 65535 && B <= 65535 && !force_gather) {
-    PMT_CUDA_OK(cudaFuncSetAttribute(upsample_softargmin_tiled_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+  if (upsample_tiled_plan(a, &fr_max, &fc_max, &tile_bytes) && !force_gather) {
+    PMT_CUDA_OK(cudaFuncSetAttribute(upsample_softargmin_tiled_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      64 * 1024));
-    upsample_softargmin_tiled_kernel<<<dim3((unsigned)gx, (unsigned)gy, (unsigned)B), kUpTH * kUpTW, tile_bytes, st>>>(
-        lowres, out, lse, a, fr_max, fc_max);
+    upsample_softargmin_tiled_kernel<false><<<dim3((unsigned)gx, (unsigned)gy, (unsigned)B), kUpTH * kUpTW, tile_bytes, st>>>(
+        lowres, out, lse, a, fr_max, fc_max, nullptr, nullptr);
     PMT_LAUNCH_OK("upsample_softargmin_tiled_kernel");
     return PMT_OK;
   }
   upsample_softargmin_fwd_kernel<<<stream_grid(total), 256, (size_t)D * 8, st>>>(lowres, out, lse, a, total);
   PMT_LAUNCH_OK("upsample_softargmin_fwd_kernel");
+  return PMT_OK;
+}
+
+// 1 if the fused backward supports this shape (tiled plan fits, adjoint windows fit), else the caller re-materialises
+int upsample_softargmin_bwd_supported(int B, int Dq, int Hq, int Wq, int D, int H, int W) {
+  if (B <= 0 || D <= 0 || H <= 0 || W <= 0 || D > 4096) return 0;
+  UpArgs a{B, Dq, Hq, Wq, D, H, W, (float)Dq / (float)D, (float)Hq / (float)H, (float)Wq / (float)W};
+  int fr_max, fc_max;
+  size_t bytes;
+  if (!upsample_tiled_plan(a, &fr_max, &fc_max, &bytes)) return 0;
+  const float win_h = 2.f / a.sh + 5.f, win_w = 2.f / a.sw + 5.f;
+  return win_h <= (float)kAdjMaxWin && win_w <= (float)kAdjMaxWin ? 1 : 0;
+}
+
+int launch_upsample_softargmin_bwd(const float* lowres, const float* out, const float* lse, const float* gout, float* U,
+                                   float* glow, int B, int Dq, int Hq, int Wq, int D, int H, int W, cudaStream_t st) {
+  if ((int64_t)B * Dq * Hq * Wq == 0) return PMT_OK;
+  PMT_CHECK_ARG(upsample_softargmin_bwd_supported(B, Dq, Hq, Wq, D, H, W) == 1,
+                "upsample_softargmin backward: shape not supported by the fused kernels");
+  UpArgs a{B, Dq, Hq, Wq, D, H, W, (float)Dq / (float)D, (float)Hq / (float)H, (float)Wq / (float)W};
+  int fr_max, fc_max;
+  size_t tile_bytes;
+  upsample_tiled_plan(a, &fr_max, &fc_max, &tile_bytes);
+  const int64_t gy = ceil_div64(H, kUpTH), gx = ceil_div64(W, kUpTW);
+  PMT_CUDA_OK(cudaFuncSetAttribute(upsample_softargmin_tiled_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   64 * 1024));
+  upsample_softargmin_tiled_kernel<true><<<dim3((unsigned)gx, (unsigned)gy, (unsigned)B), kUpTH * kUpTW, tile_bytes, st>>>(
+      lowres, const_cast<float*>(out), const_cast<float*>(lse), a, fr_max, fc_max, gout, U);
+  PMT_LAUNCH_OK("upsample_softargmin_tiled_kernel<bwd>");
+  const int64_t total = (int64_t)B * Dq * Hq * Wq;
+  upsample_adjoint2d_kernel<<<stream_grid(total), 256, 0, st>>>(U, glow, a, total);
+  PMT_LAUNCH_OK("upsample_adjoint2d_kernel");
   return PMT_OK;
 }
 
