@@ -158,5 +158,7 @@ def test_upsample_softargmin_vs_oracle_and_unfused(pmt, B, Dq, Hq, Wq, scale):
     pmt.upsample_softargmin(cf, D, (H, W)).backward(g)
     ref.backward(g)
     assert cf.grad.shape == cr.grad.shape
-    # (+1e-6: with a single source plane the gradient is exactly 0; autograd returns round-off noise of ~4e-7)
-    assert float((cf.grad - cr.grad).abs().max()) <= 1e-4 * float(cr.grad.abs().max()) + 1e-6
+    # (absolute floor: with a single source plane the gradient is exactly 0 and autograd returns the round-off of a
+    # few hundred atomically added O(1) terms, ~1e-6 and different from run to run)
+    err = float((cf.grad - cr.grad).abs().max())
+    assert err <= 1e-4 * float(cr.grad.abs().max()) + 5e-5, (err, float(cr.grad.abs().max()))
