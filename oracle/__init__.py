@@ -181,3 +181,17 @@ def upsample_softargmin_fwd(lowres, maxdisp, size):
     out = np.empty((B, H, W), dtype=np.float32)
     lib().pmt_oracle_upsample_softargmin_fwd(_p(lowres), _p(out), B, Dq, Hq, Wq, int(maxdisp), H, W)
     return out
+
+
+def upsample_softargmin_bwd(lowres, gout, maxdisp, size):
+    """Gradient of sum(gout * pred) w.r.t. the low-res logits (same shape as `lowres`)."""
+    lowres = _c(lowres)
+    shape = lowres.shape
+    if lowres.ndim == 5:
+        lowres = np.ascontiguousarray(lowres[:, 0])
+    gout = _c(gout)
+    B, Dq, Hq, Wq = lowres.shape
+    H, W = int(size[0]), int(size[1])
+    glow = np.empty_like(lowres)
+    lib().pmt_oracle_upsample_softargmin_bwd(_p(lowres), _p(gout), _p(glow), B, Dq, Hq, Wq, int(maxdisp), H, W)
+    return glow.reshape(shape)

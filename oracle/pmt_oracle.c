@@ -335,6 +335,61 @@ void pmt_oracle_upsample_softargmin_fwd(const float* low, float* out, int B, int
   }
 }
 
+/* f1 backward: gradient of sum(gout * pred) w.r.t. the low-res logits, by the chain rule through the same steps
+ * (autograd of the reference sequence): g_x[d] = gout * p_d * (d - pred), scattered onto the 8 trilinear taps.
+ * Serial scatter in double (the oracle is not the thing measured).  Pinned by gcost3 of upsoftargmin_small.npz. */
+void pmt_oracle_upsample_softargmin_bwd(const float* low, const float* gout, float* glow, int B, int Dq, int Hq, int Wq,
+                                        int D, int H, int W) {
+  const float sd = (float)Dq / (float)D, sh = (float)Hq / (float)H, sw = (float)Wq / (float)W;
+  const int64_t qplane = (int64_t)Hq * Wq, nlow = (int64_t)B * Dq * qplane;
+  double* acc = (double*)calloc((size_t)nlow, sizeof(double));
+  float* c = (float*)malloc(sizeof(float) * (size_t)D);
+  for (int64_t q = 0; q < (int64_t)B * H * W; ++q) {
+    const int w = (int)(q % W), h = (int)((q / W) % H), b = (int)(q / ((int64_t)W * H));
+    int h0, h1, w0, w1;
+    float hl0, hl1, wl0, wl1;
+    up_src(sh, h, Hq, &h0, &h1, &hl0, &hl1);
+    up_src(sw, w, Wq, &w0, &w1, &wl0, &wl1);
+    const float* base = low + (int64_t)b * Dq * qplane;
+    float m = -INFINITY;
+    for (int d = 0; d < D; ++d) {
+      int t0, t1;
+      float tl0, tl1;
+      up_src(sd, d, Dq, &t0, &t1, &tl0, &tl1);
+      const float* p0 = base + (int64_t)t0 * qplane;
+      const float* p1 = base + (int64_t)t1 * qplane;
+      const float a0 = hl0 * (wl0 * p0[h0 * Wq + w0] + wl1 * p0[h0 * Wq + w1]) +
+                       hl1 * (wl0 * p0[h1 * Wq + w0] + wl1 * p0[h1 * Wq + w1]);
+      const float a1 = hl0 * (wl0 * p1[h0 * Wq + w0] + wl1 * p1[h0 * Wq + w1]) +
+                       hl1 * (wl0 * p1[h1 * Wq + w0] + wl1 * p1[h1 * Wq + w1]);
+      c[d] = tl0 * a0 + tl1 * a1;
+      m = fmaxf(m, c[d]);
+    }
+    double ssum = 0.0, pred = 0.0;
+    for (int d = 0; d < D; ++d) ssum += exp((double)c[d] - (double)m);
+    for (int d = 0; d < D; ++d) pred += exp((double)c[d] - (double)m) / ssum * (double)d;
+    double* ab = acc + (int64_t)b * Dq * qplane;
+    for (int d = 0; d < D; ++d) {
+      int t0, t1;
+      float tl0, tl1;
+      up_src(sd, d, Dq, &t0, &t1, &tl0, &tl1);
+      const double gx = (double)gout[q] * (exp((double)c[d] - (double)m) / ssum) * ((double)d - pred);
+      const int ts[2] = {t0, t1};
+      const double tw[2] = {tl0, tl1};
+      const int hs[2] = {h0, h1};
+      const double hw[2] = {hl0, hl1};
+      const int ws[2] = {w0, w1};
+      const double ww[2] = {wl0, wl1};
+      for (int i = 0; i < 2; ++i)
+        for (int j = 0; j < 2; ++j)
+          for (int k = 0; k < 2; ++k) ab[(int64_t)ts[i] * qplane + hs[j] * Wq + ws[k]] += gx * tw[i] * hw[j] * ww[k];
+    }
+  }
+  for (int64_t i = 0; i < nlow; ++i) glow[i] = (float)acc[i];
+  free(acc);
+  free(c);
+}
+
 /* ------------------------------------------------------------------------------------------
  * a4. apply_disparity(img, x_offset, wrap_mode='edge') -- models/torch_dsnet.py:10-86.
  * Every arithmetic step is kept in fp32 exactly as the reference does it, INCLUDING the flat

@@ -149,6 +149,8 @@ class PairedSyncBatchNorm(nn.BatchNorm2d):
             return F.relu(y) if self.relu else y
         if x.size(0) % 2:
             raise ValueError("PairedSyncBatchNorm expects an even batch: [left; right]")
+        if not x.is_cuda:
+            raise RuntimeError(f"PairedSyncBatchNorm got a tensor on {x.device}: training needs CUDA tensors (no CPU path)")
         if self.num_batches_tracked is not None:
             self.num_batches_tracked.add_(2)
         dist = torch.distributed
@@ -173,6 +175,7 @@ def pair_batchnorms(module: nn.Module, fuse_relu: bool = True) -> nn.Module:
         if isinstance(child, (nn.BatchNorm2d, nn.SyncBatchNorm)) and not isinstance(child, PairedSyncBatchNorm):
             new = PairedSyncBatchNorm(child.num_features, child.eps, child.momentum, child.affine, child.track_running_stats)
             new.weight, new.bias = child.weight, child.bias
+            new.training = child.training
             new.running_mean, new.running_var, new.num_batches_tracked = (child.running_mean, child.running_var,
                                                                           child.num_batches_tracked)
             if fuse_relu and i + 1 < len(names) and isinstance(getattr(module, names[i + 1]), nn.ReLU):

@@ -87,3 +87,31 @@ def test_product_never_imports_oracle():
                     src = fh.read()
                 assert not re.search(r"^\s*(import|from)\s+oracle\b", src, flags=re.M), f
                 assert "libpmt_oracle" not in src, f
+
+
+def test_pair_batchnorms_conversion_host_logic(built):
+    """pair_batchnorms: parameters/buffers are shared (not copied), a ReLU that follows a BN is taken over, and in eval
+    mode (no kernel involved) the paired module computes what BN + ReLU computed."""
+    import torch
+    from torch import nn
+
+    import pmt_learning_for_semantic_segmentation_and_disparity_b200 as pmt
+
+    torch.manual_seed(0)
+    net = nn.Sequential(nn.Conv2d(3, 4, 3, padding=1), nn.BatchNorm2d(4), nn.ReLU(inplace=True),
+                        nn.Sequential(nn.Conv2d(4, 4, 1), nn.BatchNorm2d(4)), nn.ReLU())
+    with torch.no_grad():
+        net[1].running_mean.uniform_(-1, 1), net[1].running_var.uniform_(0.5, 2), net[1].weight.uniform_(0.5, 1.5)
+    x = torch.randn(4, 3, 6, 8)
+    net.eval()
+    want = net(x)
+    bn_w, bn_rm = net[1].weight, net[1].running_mean
+    pmt.pair_batchnorms(net)
+    assert isinstance(net[1], pmt.PairedSyncBatchNorm) and net[1].relu and isinstance(net[2], nn.Identity)
+    assert isinstance(net[3][1], pmt.PairedSyncBatchNorm) and not net[3][1].relu   # its ReLU is not a sibling: left alone
+    assert isinstance(net[4], nn.ReLU)
+    assert net[1].weight is bn_w and net[1].running_mean is bn_rm
+    assert torch.allclose(net(x), want, atol=1e-6)
+    net.train()
+    with pytest.raises(ValueError):
+        net[1](torch.randn(3, 4, 6, 8))                                            # odd batch cannot be [left; right]

@@ -155,3 +155,11 @@ def test_upsample_softargmin_oracle_vs_reference(golden_dir):
     d = load(golden_dir, "upsoftargmin_small.npz")
     out = oracle.upsample_softargmin_fwd(d["cost3"], int(d["maxdisp"]), d["size"])
     assert rel_err(out, d["pred"]) <= 1e-5
+
+
+def test_upsample_softargmin_bwd_oracle_vs_reference_autograd(golden_dir):
+    d = load(golden_dir, "upsoftargmin_small.npz")
+    g = oracle.upsample_softargmin_bwd(d["cost3"], d["gpred"], int(d["maxdisp"]), d["size"])
+    assert g.shape == d["gcost3"].shape
+    assert rel_err(g, d["gcost3"]) <= 1e-5
+
