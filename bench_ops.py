@@ -17,16 +17,19 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 
-def main():
+def run_ops(iters: int = 50, device_index: int = 0, emit=None, quick: bool = False):
+    """Time every op; returns the list of result dicts (emit(d) is called per line).  quick=True skips the
+    CUDA-core / plain-TF32 engine rows and the ATen comparison rows (what bench.py folds into its `ops` record)."""
     import torch
 
     import pmt_learning_for_semantic_segmentation_and_disparity_b200 as pmt
 
-    ap = argparse.ArgumentParser()
-    ap.add_argument("--iters", type=int, default=50)
-    ap.add_argument("--out", default="")
-    args = ap.parse_args()
-    dev = torch.device("cuda:0")
+    class _A:
+        pass
+
+    args = _A()
+    args.iters = iters
+    dev = torch.device("cuda", device_index)
     lib = pmt.load_library()
     hbm = 6525.2
     mp = os.path.join(ROOT, "MEASURED_PEAKS.json")
@@ -55,7 +58,8 @@ def main():
         if extra:
             d.update(extra)
         lines.append(d)
-        print(json.dumps(d), flush=True)
+        if emit is not None:
+            emit(d)
 
     # ---- correlation engines ------------------------------------------------------------------------
     for (B, C, H, W, P, tag) in [(4, 64, 256, 512, 192, "headline C=64 256x512 D=192"),
@@ -74,6 +78,9 @@ def main():
                    "simt": ("pmt_corr1d_fwd_simt_f32", "pmt_corr1d_bwd_simt_f32", ()),
                    "tf32": ("pmt_corr1d_fwd_tc_f32", "pmt_corr1d_bwd_tc_f32", (1,))}
         for name, (ff, bf, ex) in engines.items():
+            if quick and name != "auto":
+                continue
+
             def fwd(i, ff=ff, ex=ex):
                 s = S[i]
                 return getattr(lib, ff)(vp(s["L"]), vp(s["R"]), vp(s["out"]), B, C, H, W, P, 1, *ex, sp)
@@ -120,8 +127,9 @@ def main():
     report("dispreg_bwd", "config3", ms, cb + ob, B)
     # the reference's own op sequence on the same GPU (softmax -> repeat ramp -> mul -> sum), for context
     ramp = torch.arange(D, device=dev, dtype=torch.float32).view(1, D, 1, 1)
-    ms = timed(lambda i: torch.sum(torch.softmax(c[i], dim=1) * ramp.repeat(B, 1, H, W), 1), 2)
-    report("softargmin_fwd[ATen sequence of the reference]", "config3", ms, cb + 2 * ob, B)
+    if not quick:
+        ms = timed(lambda i: torch.sum(torch.softmax(c[i], dim=1) * ramp.repeat(B, 1, H, W), 1), 2)
+        report("softargmin_fwd[ATen sequence of the reference]", "config3", ms, cb + 2 * ob, B)
     # f1: trilinear x4 upsample fused into the soft-argmin vs the reference sequence (upsample -> softmax -> regression)
     low = [3.0 * torch.randn(B, 1, D // 4, H // 4, W // 4, device=dev) for _ in range(2)]
     lb = 4 * B * (D // 4) * (H // 4) * (W // 4)
@@ -140,8 +148,9 @@ def main():
         up = torch.nn.functional.interpolate(low[i], size=[D, H, W], mode="trilinear", align_corners=False)[:, 0]
         return torch.sum(torch.softmax(up, dim=1) * ramp.repeat(B, 1, H, W), 1)
 
-    ms = timed(unfused, 2)
-    report("upsample+softmax+regression [ATen sequence of the reference]", "config3", ms, lb + ob, B)
+    if not quick:
+        ms = timed(unfused, 2)
+        report("upsample+softmax+regression [ATen sequence of the reference]", "config3", ms, lb + ob, B)
     lowg = low[0].clone().requires_grad_(True)
 
     def unfused_fb(i):
@@ -149,8 +158,9 @@ def main():
         up = torch.nn.functional.interpolate(lowg, size=[D, H, W], mode="trilinear", align_corners=False)[:, 0]
         torch.sum(torch.softmax(up, dim=1) * ramp.repeat(B, 1, H, W), 1).backward(go)
 
-    ms = timed(unfused_fb, 1)
-    report("upsample+softmax+regression fwd+bwd [ATen autograd]", "config3", ms, 2 * lb + 3 * ob, B)
+    if not quick:
+        ms = timed(unfused_fb, 1)
+        report("upsample+softmax+regression fwd+bwd [ATen autograd]", "config3", ms, 2 * lb + 3 * ob, B)
     del c, gc
 
     # ---- warp (config 4: 540x960, C=3; production 256x512 C=2) --------------------------------------
@@ -170,6 +180,16 @@ def main():
         ms = timed(wb, 1)
         report("warp1d_bwd (+zero fill of gimg)", f"N={N} C={C} {H}x{W}", ms, 4 * N * H * W * (3 * C + 2), N)
 
+    return lines
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--iters", type=int, default=50)
+    ap.add_argument("--out", default="")
+    ap.add_argument("--quick", action="store_true")
+    args = ap.parse_args()
+    lines = run_ops(args.iters, 0, lambda d: print(json.dumps(d), flush=True), args.quick)
     if args.out:
         with open(args.out, "w") as f:
             for d in lines:

@@ -34,6 +34,7 @@ def main():
     ap.add_argument("--no-pair", action="store_true",
                     help="run the siamese tower twice (one SyncBatchNorm collective per call) instead of once over "
                          "[left; right] with per-half statistics and one collective per layer")
+    ap.add_argument("--json-out", default="", help="also write the JSON record to this file (rank 0)")
     ap.add_argument("--graph", action="store_true", help="(default) capture the whole step, NCCL collectives included, "
                                                          "in one CUDA graph")
     args = ap.parse_args()
@@ -66,13 +67,16 @@ def main():
     value, ms = sharding.throughput(world, args.batch * args.steps, e0.elapsed_time(e1))
     if world.is_main:
         n_params = sum(p.numel() for p in model.parameters())
-        print(json.dumps({"metric": "SDNetLite training step pairs/s (256x512, batch 4/GPU, DDP+SyncBN)", "value": value,
-                          "unit": "pairs/s", "n_gpus": world.world_size, "steps": args.steps,
-                          "ms_per_step": ms / args.steps, "scaling": "weak", "global_batch": args.batch * world.world_size,
-                          "params": n_params, "loss": float(loss.detach()), "sync_bn": not args.no_sync_bn,
-                          "cuda_graph": use_graph, "paired_tower": not args.no_pair and not args.no_sync_bn,
-                          "collectives": "DDP gradient all-reduce + SyncBatchNorm statistics (NCCL); none in the hot-path ops"}),
-              flush=True)
+        rec = {"metric": "SDNetLite training step pairs/s (256x512, batch 4/GPU, DDP+SyncBN)", "value": value,
+               "unit": "pairs/s", "n_gpus": world.world_size, "steps": args.steps,
+               "ms_per_step": ms / args.steps, "scaling": "weak", "global_batch": args.batch * world.world_size,
+               "params": n_params, "loss": float(loss.detach()), "sync_bn": not args.no_sync_bn,
+               "cuda_graph": use_graph, "paired_tower": not args.no_pair and not args.no_sync_bn,
+               "collectives": "DDP gradient all-reduce + SyncBatchNorm statistics (NCCL); none in the hot-path ops"}
+        print(json.dumps(rec), flush=True)
+        if args.json_out:
+            with open(args.json_out, "w") as f:
+                json.dump(rec, f)
     if use_graph and world.distributed:
         # A CUDA graph that holds captured NCCL kernels keeps the communicator busy: destroy_process_group() was
         # observed to block forever behind it (that -- not the capture -- was the "hang" of the first attempts).

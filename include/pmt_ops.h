@@ -186,8 +186,6 @@ int pmt_corr1d_fwd_bwd_host_f32(const float* in1_host, const float* in2_host, co
  * of `bytes` bytes src->dst with a float4 grid-stride kernel, returns GB/s (read+write).
  * ------------------------------------------------------------------------------------------- */
 int pmt_probe_fp32_fma(int iters, double* tflops, void* stream);
-/* development hook (profiling builds only): which=0 sets the device buffer for per-role wait-cycle counters */
-int pmt_debug_set_ptr(int which, void* p);
 int pmt_probe_copy(const void* src, void* dst, int64_t bytes, double* gbps, void* stream);
 
 #ifdef __cplusplus

@@ -32,7 +32,8 @@ def build_library(force: bool = False, verbose: bool = False) -> str:
     if not force and not needs_build():
         return LIB_PATH
     cmd = [_nvcc(), "-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
-           "-Xcompiler", "-fPIC", "-shared", "-I", INCLUDE, "-I", CSRC, "-Xptxas", "-v", *(["-DPMT_BWD_PROFILE"] if os.environ.get("PMT_BWD_PROFILE") else []),
+           "-Xcompiler", "-fPIC", "-shared", "-I", INCLUDE, "-I", CSRC, "-Xptxas", "-v", *(["-DPMT_BWD_PROFILE", "-DPMT_DEV_KNOBS"] if os.environ.get("PMT_BWD_PROFILE") else []),
+           *(["-DPMT_DEV_KNOBS"] if os.environ.get("PMT_DEV_KNOBS") and not os.environ.get("PMT_BWD_PROFILE") else []),
            "-o", LIB_PATH] + [os.path.join(CSRC, s) for s in SOURCES]
     res = subprocess.run(cmd, capture_output=True, text=True)
     log = os.path.join(PKG_DIR, "build.log")

@@ -48,7 +48,6 @@ _SIGNATURES = {
     "pmt_probe_fp32_fma": [_I, ctypes.POINTER(ctypes.c_double), _P],
     "pmt_probe_copy": [_P, _P, ctypes.c_int64, ctypes.POINTER(ctypes.c_double), _P],
     "pmt_device_supported": [_I],
-    "pmt_debug_set_ptr": [_I, _P],
     "pmt_version": [],
 }
 EXPORTED_SYMBOLS = sorted(list(_SIGNATURES) + ["pmt_last_error"])

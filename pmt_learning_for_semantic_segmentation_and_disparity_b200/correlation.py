@@ -64,6 +64,10 @@ class SpatialCorrelationSamplerFunction(Function):
         dpH, dpW = U.pair(dilation_patch, "dilation_patch")
         if pH < 1 or pW < 1 or dpH < 1 or dpW < 1:
             raise ValueError("patch_size and dilation_patch must be >= 1")
+        if (pH % 2 == 0 and dpH > 1) or (pW % 2 == 0 and dpW > 1):
+            raise NotImplementedError(
+                "an even patch_size combined with dilation_patch > 1 is not implemented: upstream's CPU and CUDA builds "
+                "centre that window differently and no reference call site uses it")
         in1 = U.require_cuda_f32(input1, "input1")
         in2 = U.require_cuda_f32(input2, "input2")
         if in1.dim() != 4 or in1.shape != in2.shape:

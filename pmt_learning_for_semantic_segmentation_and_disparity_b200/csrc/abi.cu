@@ -186,6 +186,13 @@ static int check_corr_args(const void* a, const void* b, const void* c, int B, i
   PMT_CHECK_ARG(a && b && c, "correlation: null pointer");
   PMT_CHECK_ARG(B >= 0 && C >= 0 && H >= 0 && W >= 0, "correlation: negative dimension");
   PMT_CHECK_ARG(pH >= 1 && pW >= 1 && dpH >= 1 && dpW >= 1, "correlation: patch/dilation_patch must be >= 1");
+  // Even patch AND dilation_patch > 1: the upstream package's CPU build centres the window at ((P-1)/2)*dil, its CUDA
+  // build (as recalled; source not available offline) at (dil*(P-1))/2 -- they differ (P=4, dil=2: 2 vs 3).  No
+  // reference call site uses that combination (every patch is odd or undilated), so it is refused rather than guessed.
+  if ((pH % 2 == 0 && dpH > 1) || (pW % 2 == 0 && dpW > 1)) {
+    set_error("correlation: an even patch size with dilation_patch > 1 is ambiguous upstream (CPU vs CUDA centre) and not implemented");
+    return PMT_ERR_UNSUPPORTED;
+  }
   return PMT_OK;
 }
 
@@ -428,40 +435,62 @@ int pmt_corr1d_fwd_bwd_host_f32(const float* in1_h, const float* in2_h, const fl
     hp.ready = true;
   }
   if (slot_elems > hp.cap) {
+    hp.cap = 0;  // nothing usable until EVERY slot has been re-allocated (a failure below leaves cap == 0)
     for (int s = 0; s < HostPipe::kSlots; ++s) {
       if (hp.buf[s]) cudaFree(hp.buf[s]);
       hp.buf[s] = nullptr;
-      PMT_CUDA_OK(cudaMalloc(&hp.buf[s], slot_elems * sizeof(float)));
     }
+    for (int s = 0; s < HostPipe::kSlots; ++s) PMT_CUDA_OK(cudaMalloc(&hp.buf[s], slot_elems * sizeof(float)));
     hp.cap = slot_elems;
   }
+  // an error inside the item loop must not leave copies / kernels of earlier items in flight on the cached streams
+  auto drain = [&hp]() {
+    for (int s = 0; s < HostPipe::kSlots; ++s) {
+      cudaStreamSynchronize(hp.h2d[s]);
+      cudaStreamSynchronize(hp.run[s]);
+      cudaStreamSynchronize(hp.d2h[s]);
+    }
+  };
+#define PMT_PIPE_OK(expr)                                                                              \
+  do {                                                                                                 \
+    cudaError_t _e = (expr);                                                                           \
+    if (_e != cudaSuccess) {                                                                           \
+      drain();                                                                                         \
+      ::pmt::set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__);    \
+      return PMT_ERR_CUDA;                                                                             \
+    }                                                                                                  \
+  } while (0)
   for (int n = 0; n < B; ++n) {
     const int s = n % HostPipe::kSlots;
     float *d1 = hp.buf[s], *d2 = d1 + fe, *g1 = d2 + fe, *g2 = g1 + fe, *dg = g2 + fe, *dout = dg + oe;
     // the slot is free again once the previous item's results have left it
-    PMT_CUDA_OK(cudaStreamWaitEvent(hp.h2d[s], hp.out_done[s], 0));
-    PMT_CUDA_OK(cudaMemcpyAsync(d1, in1_h + n * fe, fe * 4, cudaMemcpyHostToDevice, hp.h2d[s]));
-    PMT_CUDA_OK(cudaMemcpyAsync(d2, in2_h + n * fe, fe * 4, cudaMemcpyHostToDevice, hp.h2d[s]));
-    PMT_CUDA_OK(cudaMemcpyAsync(dg, gout_h + n * oe, oe * 4, cudaMemcpyHostToDevice, hp.h2d[s]));
-    PMT_CUDA_OK(cudaEventRecord(hp.in_done[s], hp.h2d[s]));
-    PMT_CUDA_OK(cudaStreamWaitEvent(hp.run[s], hp.in_done[s], 0));
-    if (int rc = pmt_corr1d_fwd_f32(d1, d2, dout, 1, C, H, W, P, dilp, hp.run[s])) return rc;
-    if (int rc = pmt_corr1d_bwd_f32(d1, d2, dg, g1, g2, 1, C, H, W, P, dilp, hp.run[s])) return rc;
-    PMT_CUDA_OK(cudaEventRecord(hp.run_done[s], hp.run[s]));
-    PMT_CUDA_OK(cudaStreamWaitEvent(hp.d2h[s], hp.run_done[s], 0));
-    PMT_CUDA_OK(cudaMemcpyAsync(out_h + n * oe, dout, oe * 4, cudaMemcpyDeviceToHost, hp.d2h[s]));
-    PMT_CUDA_OK(cudaMemcpyAsync(gin1_h + n * fe, g1, fe * 4, cudaMemcpyDeviceToHost, hp.d2h[s]));
-    PMT_CUDA_OK(cudaMemcpyAsync(gin2_h + n * fe, g2, fe * 4, cudaMemcpyDeviceToHost, hp.d2h[s]));
-    PMT_CUDA_OK(cudaEventRecord(hp.out_done[s], hp.d2h[s]));
+    PMT_PIPE_OK(cudaStreamWaitEvent(hp.h2d[s], hp.out_done[s], 0));
+    PMT_PIPE_OK(cudaMemcpyAsync(d1, in1_h + n * fe, fe * 4, cudaMemcpyHostToDevice, hp.h2d[s]));
+    PMT_PIPE_OK(cudaMemcpyAsync(d2, in2_h + n * fe, fe * 4, cudaMemcpyHostToDevice, hp.h2d[s]));
+    PMT_PIPE_OK(cudaMemcpyAsync(dg, gout_h + n * oe, oe * 4, cudaMemcpyHostToDevice, hp.h2d[s]));
+    PMT_PIPE_OK(cudaEventRecord(hp.in_done[s], hp.h2d[s]));
+    PMT_PIPE_OK(cudaStreamWaitEvent(hp.run[s], hp.in_done[s], 0));
+    if (int rc = pmt_corr1d_fwd_f32(d1, d2, dout, 1, C, H, W, P, dilp, hp.run[s])) { drain(); return rc; }
+    if (int rc = pmt_corr1d_bwd_f32(d1, d2, dg, g1, g2, 1, C, H, W, P, dilp, hp.run[s])) { drain(); return rc; }
+    PMT_PIPE_OK(cudaEventRecord(hp.run_done[s], hp.run[s]));
+    PMT_PIPE_OK(cudaStreamWaitEvent(hp.d2h[s], hp.run_done[s], 0));
+    PMT_PIPE_OK(cudaMemcpyAsync(out_h + n * oe, dout, oe * 4, cudaMemcpyDeviceToHost, hp.d2h[s]));
+    PMT_PIPE_OK(cudaMemcpyAsync(gin1_h + n * fe, g1, fe * 4, cudaMemcpyDeviceToHost, hp.d2h[s]));
+    PMT_PIPE_OK(cudaMemcpyAsync(gin2_h + n * fe, g2, fe * 4, cudaMemcpyDeviceToHost, hp.d2h[s]));
+    PMT_PIPE_OK(cudaEventRecord(hp.out_done[s], hp.d2h[s]));
   }
-  for (int s = 0; s < HostPipe::kSlots; ++s) PMT_CUDA_OK(cudaStreamSynchronize(hp.d2h[s]));
+  for (int s = 0; s < HostPipe::kSlots; ++s) PMT_PIPE_OK(cudaStreamSynchronize(hp.d2h[s]));
+#undef PMT_PIPE_OK
   return PMT_OK;
 }
 
+#ifdef PMT_DEV_KNOBS
+// development builds only (not declared in include/pmt_ops.h): device buffer for the PMT_BWD_PROFILE counters
 int pmt_debug_set_ptr(int which, void* p) {
   if (which == 0) pmt::g_bwd_prof = static_cast<long long*>(p);
   return PMT_OK;
 }
+#endif
 
 int pmt_probe_fp32_fma(int iters, double* tflops, void* stream) {
   PMT_CHECK_ARG(iters > 0 && tflops, "fp32 probe: bad argument");

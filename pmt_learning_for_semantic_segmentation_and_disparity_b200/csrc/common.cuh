@@ -51,10 +51,19 @@ inline int round_up(int a, int b) { return ceil_div(a, b) * b; }
 
 int sm_count();  // cached number of SMs of the current device
 
-// Tuning / ablation knobs read from the environment ONCE per process (getenv is a linear scan of environ; the launch
-// path of a 10-us kernel cannot afford several of them per call).  PMT_ENV_INT("NAME", default) caches per call site.
+// Tuning / ablation knobs.  They exist only in development builds (-DPMT_DEV_KNOBS, `PMT_DEV_KNOBS=1` in the
+// environment of _build.py): there PMT_ENV_INT("NAME", default) reads the environment ONCE per process and per call
+// site (getenv is a linear scan of environ; the launch path of a 10-us kernel cannot afford several per call) and
+// PMT_DBG(args, bit) tests an ablation bit of PMT_TC_DEBUG.  In the default (release) build both are compile-time
+// constants, so a stray environment variable can neither change a tile configuration nor make a kernel skip work.
 int env_int_uncached(const char* name, int dflt);
+#ifdef PMT_DEV_KNOBS
 #define PMT_ENV_INT(name, dflt) ([]() -> int { static const int v = ::pmt::env_int_uncached(name, dflt); return v; }())
+#define PMT_DBG(args, bit) ((((args).debug) & (bit)) != 0)
+#else
+#define PMT_ENV_INT(name, dflt) (dflt)
+#define PMT_DBG(args, bit) (false)
+#endif
 
 // 4-D fp32 tensor map over a dense (B,C,H,W) tensor, box = (box_w, 1, box_c, 1), zero OOB fill.
 // Returns 0 on success (error text set otherwise).

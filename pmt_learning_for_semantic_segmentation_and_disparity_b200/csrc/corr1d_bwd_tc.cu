@@ -171,7 +171,7 @@ corr1d_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmIn1, const __grid_con
 #endif
   const int band_bytes = a.Cbox * 128;
   int n_my = (a.n_tiles - cta_in_mode + ctas_of_mode - 1) / ctas_of_mode;  // tiles of this CTA
-  if (a.debug & (mode == 0 ? 4096 : 2048)) n_my = 0;   // ablation: run one gradient only
+  if (PMT_DBG(a, (mode == 0 ? 4096 : 2048))) n_my = 0;   // ablation: run one gradient only
   const int G = n_my * a.NKC;                                                            // chunks of this CTA
 
   if (tid == 0) {
@@ -213,7 +213,7 @@ corr1d_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmIn1, const __grid_con
         for (int k = 0; k < a.NKC; ++k) {
           PWAIT_RELAXED(0, &band_empty[bs], bph);
           PTRACE(0, i * a.NKC + k, 0);
-          if (a.debug & 128) {   // ablation: no band traffic
+          if PMT_DBG(a, 128) {   // ablation: no band traffic
             mbar_arrive(&band_full[bs]);
           } else {
             mbar_arrive_expect_tx(&band_full[bs], (uint32_t)band_bytes);
@@ -233,15 +233,15 @@ corr1d_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmIn1, const __grid_con
       uint32_t sph = 1;  // mode 1: parity to wait for on raw_empty[slot]
       for (int i = 0; i < n_my; ++i) {
         const TileCoord tc_ = tile_coord(a, i);
-        const bool more = !(a.debug & 512) && i + 1 < n_my;
+        const bool more = !PMT_DBG(a, 512) && i + 1 < n_my;
         const TileCoord nx = tile_coord(a, more ? i + 1 : i);
         for (int k = 0; k < a.NKC; ++k) {
           if (mode == 0) {
             if (k < a.n_gboxes) {
               // the smem ring only reaches about one tile ahead: pull the next tile's box into L2 now
-              if (more && !(a.debug & 64)) tma_prefetch_l2_4d(&tmG0, nx.x0, nx.h, 32 * k, nx.n);
+              if (more && !PMT_DBG(a, 64)) tma_prefetch_l2_4d(&tmG0, nx.x0, nx.h, 32 * k, nx.n);
               PWAIT_RELAXED(0, &raw_empty[k], ((uint32_t)i & 1u) ^ 1u);  // previous tile is done with this box
-              if (a.debug & 64) {   // ablation: no raw-g traffic
+              if PMT_DBG(a, 64) {   // ablation: no raw-g traffic
                 mbar_arrive(&raw_full[k]);
               } else {
                 mbar_arrive_expect_tx(&raw_full[k], (uint32_t)kBox0Bytes);
@@ -250,9 +250,9 @@ corr1d_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmIn1, const __grid_con
             }
           } else {
             const int p0 = a.P - 1 + m.delta - kKC * k - (kKC - 1);
-            if (more && !(a.debug & 64)) tma_prefetch_l2_4d(&tmG1, nx.x0 + m.oo + kKC * k, nx.h, p0, nx.n);
+            if (more && !PMT_DBG(a, 64)) tma_prefetch_l2_4d(&tmG1, nx.x0 + m.oo + kKC * k, nx.h, p0, nx.n);
             PWAIT_RELAXED(0, &raw_empty[slot], sph);
-            if (a.debug & 64) {
+            if PMT_DBG(a, 64) {
               mbar_arrive(&raw_full[slot]);
             } else {
               mbar_arrive_expect_tx(&raw_full[slot], (uint32_t)kRawSlot1);
@@ -275,7 +275,7 @@ corr1d_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmIn1, const __grid_con
       const uint64_t dB0 = tc::smem_desc(smem_u32(band_ring), 16, 1024, 2);
       const uint32_t a_step = (uint32_t)a.gd_slot_bytes >> 4, b_step = (uint32_t)a.band_slot_bytes >> 4;
       const uint32_t a_lo = (uint32_t)a.gd_lo_off >> 4;
-      const bool tmem_a = m.tmem_a != 0, skip = (a.debug & 16) != 0;
+      const bool tmem_a = m.tmem_a != 0, skip = PMT_DBG(a, 16) != 0;
       int gs = 0, bs = 0;
       uint32_t gph = 0, bph = 0;
       for (int i = 0; i < n_my; ++i) {
@@ -346,7 +346,7 @@ corr1d_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmIn1, const __grid_con
       float* o = dst + ((int64_t)tc_.n * a.C * a.H + tc_.h) * (int64_t)a.W + tc_.x0 + xl;
       if (kPasses == 3) {
         // 16 columns at a time (keeps registers low with 16 builder warps): D = block0 + block1 (the A_hi*B_lo part)
-        for (int cb = 0; cb < a.Cbox && !(a.debug & 8); cb += 16) {
+        for (int cb = 0; cb < a.Cbox && !PMT_DBG(a, 8); cb += 16) {
           float v[16];
           const uint32_t t0 = tmem_base + ((uint32_t)(32 * q) << 16) + (uint32_t)(buf * a.acc_cols + cb);
           tc::tmem_ld16(t0, v);
@@ -361,7 +361,7 @@ corr1d_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmIn1, const __grid_con
             if (ok && cb + cc < a.C) o[(int64_t)(cb + cc) * pstride] = v[cc];
         }
       } else {
-        for (int cb = 0; cb < a.Cbox && !(a.debug & 8); cb += 32) {
+        for (int cb = 0; cb < a.Cbox && !PMT_DBG(a, 8); cb += 32) {
           float v[32];
           tc::tmem_ld32(tmem_base + ((uint32_t)(32 * q) << 16) + (uint32_t)(buf * a.acc_cols + cb), v);
 #pragma unroll
@@ -420,7 +420,7 @@ corr1d_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmIn1, const __grid_con
 #pragma unroll
               for (int t = 0; t < 16; ++t)   // one unsigned compare covers p < 0 and p >= P
                 w[t] = (pu + (unsigned)t < Pu) ? col[(int)(pu + (unsigned)t) * kTM] : 0.f;
-              if (a.debug & 4) {
+              if PMT_DBG(a, 4) {
 #pragma unroll
                 for (int t = 0; t < 16; ++t) w[t] = 0.f;
               }
@@ -436,7 +436,7 @@ corr1d_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmIn1, const __grid_con
           } else {
 #pragma unroll
             for (int task = gw; task < 32; task += kGroupWarps) {   // 32 warp tasks per chunk: (16-byte column c4, 32-row block xb)
-              if (a.debug & 4) break;
+              if PMT_DBG(a, 4) break;
               const int c4 = task & 7, xb = task >> 3;
               const int xl = 32 * xb + lane;
               const int pb = kKC * k + 4 * c4 - m.delta - xl;  // p of column jj = 4*c4 + t is pb + t
@@ -477,7 +477,7 @@ corr1d_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmIn1, const __grid_con
           if (gw == 0) PTRACE(2 + grp, g, 2);
           const float* raw = reinterpret_cast<const float*>(smem + slot * kRawSlot1);
           { PSEC_BEGIN();
-          if (!(a.debug & 4)) {
+          if (!PMT_DBG(a, 4)) {
             // 32 warp tasks per chunk (4 Gd rows x 32 columns, lane = column); this warp takes tasks gw, gw+G, ...
             // All loads are issued before the first store so the LDS latency is paid once per chunk, not per row.
             constexpr int kTasks = 32 / kGroupWarps;
@@ -512,7 +512,7 @@ corr1d_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmIn1, const __grid_con
           PSEC_BEGIN();
           unsigned char* sb = band_ring + (size_t)bs * a.band_slot_bytes;
           const int nch = band_bytes / 16;
-          if (!(a.debug & 32)) {
+          if (!PMT_DBG(a, 32)) {
             constexpr int kStride = kGroupWarps * 32;
             const int c0 = gw * 32 + lane;
             for (int cb = c0; cb < nch; cb += 2 * kStride) {   // 2 loads in flight (C=64: one round)

@@ -136,7 +136,7 @@ corr1d_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmL, const __grid_const
       const uint32_t st_step = (uint32_t)a.stage_bytes >> 4;
       const uint32_t offB1 = (uint32_t)(kLBlocks * kBoxBytes) >> 4;
       const uint32_t offB2 = offB1 + ((uint32_t)((a.N1 / 32) * kBoxBytes) >> 4);
-      const bool skip = (a.debug & 16) != 0, two = a.N2 > 0;
+      const bool skip = PMT_DBG(a, 16) != 0, two = a.N2 > 0;
       int st = 0, ls = 0, it = 0;
       uint32_t fph = 0, lph = 0;
       for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x, ++it) {
@@ -209,7 +209,7 @@ corr1d_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmL, const __grid_const
           else tc::tma_store_wait_read<1>();
         }
         named_bar_sync(1, 128);
-        if (!(a.debug & 8)) {
+        if (!PMT_DBG(a, 8)) {
           float* col = tile_s + wl;
 #pragma unroll
           for (int jj = 0; jj < 32; ++jj) {
@@ -248,7 +248,7 @@ corr1d_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmL, const __grid_const
         // hi operand = the raw fp32 left in place (kind::tf32 ignores the low 13 mantissa bits, verified on B200:
         // the 3-term sum stays at ~1e-6); lo = x - trunc_tf32(x) is exact in fp32 and goes to the lo ring.
         // loads are issued in batches of 8 before the first store: the LDS latency is paid once per batch
-        for (int cb = t; cb < nchunks && !(a.debug & 4); cb += 8 * 128) {
+        for (int cb = t; cb < nchunks && !PMT_DBG(a, 4); cb += 8 * 128) {
           float4 x[8];
 #pragma unroll
           for (int u = 0; u < 8; ++u)

@@ -60,8 +60,8 @@ class SDNetLite(nn.Module):
         Call it AFTER nn.SyncBatchNorm.convert_sync_batchnorm (which replaces every _BatchNorm it finds, paired ones
         included, and would drop the ReLUs they have taken over), and only once."""
         self.paired_tower = True
-        pair_batchnorms(self.tower)
-        pair_batchnorms(self.reduce)
+        pair_batchnorms(self.tower, fuse_relu=True)   # torchvision _DenseLayer/_Transition + Sequential: safe to fuse
+        pair_batchnorms(self.reduce, fuse_relu=True)
         return self
 
     def forward(self, left, right):

@@ -126,11 +126,12 @@ def softargmin(cost: torch.Tensor) -> torch.Tensor:
 
 
 class _UpsampleSoftArgmin(Function):
-    """Forward: fused kernel (the (B,D,H,W) volume is never written).  Backward: fused as well when the shape fits
-    (pmt_upsample_softargmin_bwd_supported): a kernel re-interpolates the logits per pixel and writes the gradient
-    w.r.t. the Dq sampled source planes into a (B,Dq,H,W) workspace -- 4x smaller than the volume for PSMNet -- and a
-    second one applies the adjoint of the spatial interpolation.  Otherwise the backward re-materialises the volume
-    with ATen's trilinear upsample, runs the soft-argmin backward kernel and lets autograd transpose the interpolation."""
+    """Forward: fused kernel (the (B,D,H,W) volume is never written).  Backward: fused as well: a kernel
+    re-interpolates the logits per pixel and writes the gradient w.r.t. the Dq sampled source planes into a (B,Dq,H,W)
+    workspace -- 4x smaller than the volume for PSMNet -- and a second one applies the adjoint of the spatial
+    interpolation.  Shapes the fused backward does not cover (pmt_upsample_softargmin_bwd_supported() == 0: shared-memory
+    footprint, interpolation windows > 40) raise NotImplementedError when a gradient is requested -- there is no ATen
+    fallback; such a caller keeps the reference's unfused sequence (F.interpolate -> softargmin)."""
 
     @staticmethod
     def forward(ctx, cost_lowres, maxdisp, height, width):
@@ -148,30 +149,27 @@ class _UpsampleSoftArgmin(Function):
         D, H, W = int(maxdisp), int(height), int(width)
         out = torch.empty((B, H, W), device=c.device, dtype=torch.float32)
         lse = torch.empty((B, H, W), device=c.device, dtype=torch.float32)
+        if ctx.needs_input_grad[0] and U._lib.load().pmt_upsample_softargmin_bwd_supported(B, Dq, Hq, Wq, D, H, W) != 1:
+            raise NotImplementedError(
+                f"upsample_softargmin: the fused backward does not cover (Dq,Hq,Wq)=({Dq},{Hq},{Wq}) -> (D,H,W)=({D},{H},{W}); "
+                "use F.interpolate(..., mode='trilinear') followed by softargmin() for this shape (no silent fallback)")
         U.call("pmt_upsample_softargmin_fwd_f32", c.device, U.ptr(c4), U.ptr(out), U.ptr(lse), B, Dq, Hq, Wq, D, H, W)
         ctx.save_for_backward(cost_lowres, c4, out, lse)
         ctx.size = (D, H, W)
         return out
 
     @staticmethod
+    @once_differentiable
     def backward(ctx, gout):
         cost_lowres, c4, out, lse = ctx.saved_tensors
         D, H, W = ctx.size
         B, Dq, Hq, Wq = c4.shape
-        if U._lib.load().pmt_upsample_softargmin_bwd_supported(B, Dq, Hq, Wq, D, H, W) == 1:
-            g = U.require_cuda_f32(gout, "grad_output")
-            work = torch.empty((B, Dq, H, W), device=c4.device, dtype=torch.float32)
-            glow = torch.empty_like(c4)
-            U.call("pmt_upsample_softargmin_bwd_f32", c4.device, U.ptr(c4), U.ptr(out), U.ptr(lse), U.ptr(g), U.ptr(work),
-                   U.ptr(glow), B, Dq, Hq, Wq, D, H, W)
-            return glow.view(cost_lowres.shape), None, None, None
-        with torch.enable_grad():
-            c = cost_lowres.detach().requires_grad_(True)
-            c5 = c if c.dim() == 5 else c.unsqueeze(1)
-            up = torch.nn.functional.interpolate(c5, size=[D, H, W], mode="trilinear", align_corners=False)[:, 0]
-            o = softargmin(up)
-        (g,) = torch.autograd.grad(o, c, gout)
-        return g, None, None, None
+        g = U.require_cuda_f32(gout, "grad_output")
+        work = torch.empty((B, Dq, H, W), device=c4.device, dtype=torch.float32)
+        glow = torch.empty_like(c4)
+        U.call("pmt_upsample_softargmin_bwd_f32", c4.device, U.ptr(c4), U.ptr(out), U.ptr(lse), U.ptr(g), U.ptr(work),
+               U.ptr(glow), B, Dq, Hq, Wq, D, H, W)
+        return glow.view(cost_lowres.shape), None, None, None
 
 
 def upsample_softargmin(cost_lowres: torch.Tensor, maxdisp: int, size) -> torch.Tensor:

@@ -45,8 +45,9 @@ class _PairedSyncBNFn(torch.autograd.Function):
         for i, xi in enumerate(halves):                                               # left first, like two calls
             mean_all = gathered[:, 2 * i * C:(2 * i + 1) * C]
             invstd_all = gathered[:, (2 * i + 1) * C:(2 * i + 2) * C]
+            mom = momentum[i] if isinstance(momentum, (tuple, list)) else momentum
             mean, invstd = torch.batch_norm_gather_stats_with_counts(xi, mean_all, invstd_all, running_mean,
-                                                                     running_var, momentum, eps, counts.view(-1))
+                                                                     running_var, mom, eps, counts.view(-1))
             outs.append(torch.batch_norm_elemt(xi, weight, bias, mean, invstd, eps))
             saved += [mean, invstd]
         ctx.save_for_backward(x, weight, *saved, counts.to(torch.int32))
@@ -136,39 +137,82 @@ class _PairedSyncBNFusedFn(torch.autograd.Function):
 
 
 class PairedSyncBatchNorm(nn.BatchNorm2d):
-    """Drop-in for the BatchNorm2d layers of a siamese tower that is fed [left; right] in one pass (see
-    _PairedSyncBNFn).  Single process: equals calling the BatchNorm2d on each half in turn.  `fused` selects this
-    package's kernels (fp32 CUDA) over the composition of ATen ops (any dtype; the float64 reference of the tests)."""
+    """Drop-in for the BatchNorm2d / SyncBatchNorm layers of a siamese tower that is fed [left; right] in one pass (see
+    _PairedSyncBNFn).  Single process: equals calling the BatchNorm2d on each half in turn.
+
+    `fused=True` (default) runs this package's kernels and is strict: fp32 CUDA input and a numeric `momentum`, anything
+    else raises (no silent fallback).  `fused=False` is an explicit opt-in to the composition of ATen ops (any dtype; it
+    is the float64 reference of the tests and supports `momentum=None`, the cumulative moving average).
+    `process_group` restricts the statistics exchange to a sub-group like nn.SyncBatchNorm's argument of that name."""
 
     fused = True
     relu = False   # True: the ReLU that follows this BN is computed by the same kernels (pair_batchnorms sets it)
+    process_group = None
+
+    def _world(self):
+        dist = torch.distributed
+        if not (dist.is_available() and dist.is_initialized()):
+            return 1
+        return dist.get_world_size(self.process_group)
 
     def forward(self, x):
-        if not self.training:
+        use_batch_stats = self.training or self.running_mean is None   # stock BN: no running stats -> batch stats in eval
+        if not use_batch_stats:
             y = F.batch_norm(x, self.running_mean, self.running_var, self.weight, self.bias, False, 0.0, self.eps)
             return F.relu(y) if self.relu else y
         if x.size(0) % 2:
             raise ValueError("PairedSyncBatchNorm expects an even batch: [left; right]")
         if not x.is_cuda:
-            raise RuntimeError(f"PairedSyncBatchNorm got a tensor on {x.device}: training needs CUDA tensors (no CPU path)")
-        if self.num_batches_tracked is not None:
+            raise RuntimeError(f"PairedSyncBatchNorm got a tensor on {x.device}: batch statistics need CUDA tensors (no CPU path)")
+        track = self.training and self.running_mean is not None
+        ws = self._world()
+        if self.fused:
+            if x.dtype != torch.float32:
+                raise NotImplementedError(f"PairedSyncBatchNorm(fused=True) implements float32 only, got {x.dtype}; set "
+                                          ".fused = False for the ATen composition")
+            if self.momentum is None and track:
+                raise NotImplementedError("PairedSyncBatchNorm(fused=True) needs a numeric momentum; momentum=None "
+                                          "(cumulative average) is implemented by .fused = False")
+            if track and self.num_batches_tracked is not None:
+                self.num_batches_tracked.add_(2)
+            if x.data_ptr() % 16:
+                x = x.clone(memory_format=torch.contiguous_format)   # an offset view: the kernels read 16-byte vectors
+            return _PairedSyncBNFusedFn.apply(x, self.weight, self.bias, self.running_mean if track else None,
+                                              self.running_var if track else None, self.eps,
+                                              self.momentum if self.momentum is not None else 0.0, self.process_group, ws,
+                                              self.relu)
+        if self.momentum is None and track:
+            # cumulative moving average: the left call sees num_batches_tracked+1, the right call +2 (two calls of one BN)
+            n = int(self.num_batches_tracked) if self.num_batches_tracked is not None else 0
+            factors = (1.0 / (n + 1), 1.0 / (n + 2))
+        else:
+            factors = (self.momentum if self.momentum is not None else 0.0,) * 2
+        if track and self.num_batches_tracked is not None:
             self.num_batches_tracked.add_(2)
-        dist = torch.distributed
-        ws = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
-        fused = (self.fused and x.is_cuda and x.dtype == torch.float32 and self.momentum is not None
-                 and x.data_ptr() % 16 == 0)
-        if fused:
-            return _PairedSyncBNFusedFn.apply(x, self.weight, self.bias, self.running_mean, self.running_var, self.eps,
-                                              self.momentum, None, ws, self.relu)
-        y = _PairedSyncBNFn.apply(x, self.weight, self.bias, self.running_mean, self.running_var, self.eps, self.momentum,
-                                  None, ws)
+        y = _PairedSyncBNFn.apply(x, self.weight, self.bias, self.running_mean if track else None,
+                                  self.running_var if track else None, self.eps, factors, self.process_group, ws)
         return F.relu(y) if self.relu else y
 
 
-def pair_batchnorms(module: nn.Module, fuse_relu: bool = True) -> nn.Module:
+# Parents whose registration order is their call order, so "the next registered sibling is an nn.ReLU" really means
+# "this ReLU is applied to this BN's output and to nothing else": nn.Sequential and torchvision's DenseNet blocks
+# (norm1 -> relu1 -> conv1 -> norm2 -> relu2 -> conv2).  ResNet-style blocks register ONE relu after bn1 and apply it
+# again after the residual add -- replacing it would silently drop that second use -- so nothing else is ever fused.
+_RELU_FUSION_PARENTS = ("_DenseLayer", "_Transition")
+
+
+def _may_fuse_relu(parent: nn.Module) -> bool:
+    return isinstance(parent, nn.Sequential) or type(parent).__name__ in _RELU_FUSION_PARENTS
+
+
+def pair_batchnorms(module: nn.Module, fuse_relu: bool = False) -> nn.Module:
     """Replace every BatchNorm2d / SyncBatchNorm below `module` by a PairedSyncBatchNorm that shares its parameters and
-    buffers.  With fuse_relu, a BN whose NEXT sibling (registration order = call order in Sequential, torchvision's
-    _DenseLayer and _Transition) is an nn.ReLU takes the ReLU over (the sibling becomes nn.Identity)."""
+    buffers (and keeps a converted SyncBatchNorm's process_group).
+
+    fuse_relu (opt-in): a BN whose NEXT registered sibling is an nn.ReLU takes that ReLU over (the sibling becomes
+    nn.Identity) -- only inside nn.Sequential containers and torchvision's _DenseLayer / _Transition, where registration
+    order is call order and the ReLU has no other use.  A ReLU that is a shared attribute of a hand-written block
+    (ResNet BasicBlock/Bottleneck: `self.relu` after bn1 AND after the residual add) is never touched."""
     names = [n for n, _ in module.named_children()]
     for i, name in enumerate(names):
         child = getattr(module, name)
@@ -178,7 +222,9 @@ def pair_batchnorms(module: nn.Module, fuse_relu: bool = True) -> nn.Module:
             new.training = child.training
             new.running_mean, new.running_var, new.num_batches_tracked = (child.running_mean, child.running_var,
                                                                           child.num_batches_tracked)
-            if fuse_relu and i + 1 < len(names) and isinstance(getattr(module, names[i + 1]), nn.ReLU):
+            new.process_group = getattr(child, "process_group", None)
+            if (fuse_relu and _may_fuse_relu(module) and i + 1 < len(names)
+                    and isinstance(getattr(module, names[i + 1]), nn.ReLU)):
                 new.relu = True
                 setattr(module, names[i + 1], nn.Identity())
             setattr(module, name, new)

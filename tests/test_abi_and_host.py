@@ -106,7 +106,7 @@ def test_pair_batchnorms_conversion_host_logic(built):
     net.eval()
     want = net(x)
     bn_w, bn_rm = net[1].weight, net[1].running_mean
-    pmt.pair_batchnorms(net)
+    pmt.pair_batchnorms(net, fuse_relu=True)
     assert isinstance(net[1], pmt.PairedSyncBatchNorm) and net[1].relu and isinstance(net[2], nn.Identity)
     assert isinstance(net[3][1], pmt.PairedSyncBatchNorm) and not net[3][1].relu   # its ReLU is not a sibling: left alone
     assert isinstance(net[4], nn.ReLU)
@@ -115,3 +115,61 @@ def test_pair_batchnorms_conversion_host_logic(built):
     net.train()
     with pytest.raises(ValueError):
         net[1](torch.randn(3, 4, 6, 8))                                            # odd batch cannot be [left; right]
+
+
+def test_pair_batchnorms_never_drops_a_shared_relu(built):
+    """ResNet-style blocks register ONE nn.ReLU right after bn1 and apply it again after the residual add
+    (reference: models/Resnet.py BasicBlock/Bottleneck).  The conversion must leave that ReLU alone -- with the default
+    AND with fuse_relu=True -- and the default must not fuse anything."""
+    import torch
+    from torch import nn
+
+    import pmt_learning_for_semantic_segmentation_and_disparity_b200 as pmt
+
+    class BasicBlock(nn.Module):
+        def __init__(self, c):
+            super().__init__()
+            self.conv1 = nn.Conv2d(c, c, 3, padding=1, bias=False)
+            self.bn1 = nn.BatchNorm2d(c)
+            self.relu = nn.ReLU(inplace=True)
+            self.conv2 = nn.Conv2d(c, c, 3, padding=1, bias=False)
+            self.bn2 = nn.BatchNorm2d(c)
+
+        def forward(self, x):
+            out = self.relu(self.bn1(self.conv1(x)))
+            out = self.bn2(self.conv2(out))
+            return self.relu(out + x)
+
+    torch.manual_seed(1)
+    for fuse in (False, True):
+        blk = BasicBlock(4).eval()
+        with torch.no_grad():
+            blk.bn1.running_mean.uniform_(-1, 1), blk.bn2.running_mean.uniform_(-1, 1)
+        x = torch.randn(2, 4, 6, 8)
+        want = blk(x)
+        pmt.pair_batchnorms(blk, fuse_relu=fuse)
+        assert isinstance(blk.bn1, pmt.PairedSyncBatchNorm) and isinstance(blk.relu, nn.ReLU) and not blk.bn1.relu
+        got = blk(x)
+        assert torch.equal(got, want) and float(got.min()) >= 0.0
+    seq = nn.Sequential(nn.Conv2d(3, 4, 1), nn.BatchNorm2d(4), nn.ReLU())
+    pmt.pair_batchnorms(seq)                                       # default: no fusion even where it would be safe
+    assert isinstance(seq[2], nn.ReLU) and not seq[1].relu
+
+
+def test_paired_batchnorm_host_contract(built):
+    """Drop-in details of the converted layer: process_group of a SyncBatchNorm is kept; eval without running
+    statistics needs batch statistics (so it raises on CPU instead of calling F.batch_norm(training=False) on None);
+    fused=True refuses what it does not implement instead of falling back."""
+    import torch
+    from torch import nn
+
+    import pmt_learning_for_semantic_segmentation_and_disparity_b200 as pmt
+
+    sbn = nn.SyncBatchNorm(4)
+    sbn.process_group = "sentinel-group"
+    holder = nn.Sequential(sbn)
+    pmt.pair_batchnorms(holder)
+    assert holder[0].process_group == "sentinel-group"
+    bn = pmt.PairedSyncBatchNorm(4, track_running_stats=False).eval()
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        bn(torch.randn(2, 4, 3, 3))                               # batch statistics even in eval: needs the CUDA kernels

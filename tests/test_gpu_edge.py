@@ -33,3 +33,18 @@ def test_zero_rows_and_single_pixel(pmt):
     assert torch.allclose(out[0, 0, 0], (a * b).sum(1)[0], atol=1e-5)
     cost = torch.randn(1, 1, 1, 1, device=DEV)
     assert float(pmt.softargmin(cost)) == 0.0      # a single plane: probability 1 at disparity 0
+
+
+def test_even_patch_with_dilation_is_refused(pmt):
+    """Upstream's CPU and CUDA builds centre an even, dilated patch differently; no reference call site uses it, so the
+    op refuses it (Python surface and C ABI) instead of guessing."""
+    import ctypes
+
+    a = torch.zeros(1, 2, 4, 8, device="cuda:0")
+    with pytest.raises(NotImplementedError):
+        pmt.spatial_correlation_sample(a, a, patch_size=(1, 4), dilation_patch=2)
+    lib = pmt.load_library()
+    out = torch.empty(1, 1, 4, 4, 8, device="cuda:0")
+    vp = lambda t: ctypes.c_void_p(t.data_ptr())
+    assert lib.pmt_corr_fwd_f32(vp(a), vp(a), vp(out), 1, 2, 4, 8, 1, 4, 1, 2, None) == 3   # PMT_ERR_UNSUPPORTED
+    assert b"even patch" in lib.pmt_last_error()
