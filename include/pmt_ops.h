@@ -46,8 +46,8 @@ int pmt_device_supported(int dev);
  *
  * pmt_corr1d_{fwd,bwd}_f32: the 1 x P horizontal patch (the hot path; `-corrType 1dcorr`), fp32-accurate
  *   results from the fastest engine that fits: tensor cores with the 3xTF32 split (W%4==0, 16-byte
- *   pointers, dilp==1, P<=193, C<=128 for the backward) -> CUDA-core TMA-tiled kernels -> generic
- *   kernels.  Backward is a deterministic gather on every engine (bit-reproducible run to run).
+ *   pointers, dilp==1; forward P<=193, backward P<=256; any C -- channel blocks of 128 in the backward) ->
+ *   CUDA-core TMA-tiled kernels -> generic kernels.  Backward is a deterministic gather on every engine (bit-reproducible run to run).
  * pmt_corr1d_{fwd,bwd}_simt_f32: force the CUDA-core engines (fp32 FFMA).
  * pmt_corr1d_{fwd,bwd}_tc_f32: force the tensor-core engine (see below).
  * pmt_corr_*: any (patchH, patchW, dilation_patch) -- generic CUDA kernels (2-D 17x17 patches of
@@ -131,14 +131,44 @@ int pmt_upsample_softargmin_bwd_f32(const float* lowres, const float* out, const
  *   `out` is written in the reference's storage order [C][N][H][W] when out_cnhw != 0 (the
  *   reference returns that buffer permuted to (N,C,H,W), torch_dsnet.py:84), else [N][C][H][W].
  *   The flat gather index is formed in fp32 exactly as torch_dsnet.py:59-70 does (only matters when
- *   N*H*W >= 2^24).  Backward: gimg must be ZEROED by the caller (scatter target, fp32 atomics);
+ *   N*H*W >= 2^24).  Backward: every element of gimg is WRITTEN by the call (no zero fill by the caller).
+ *   While N*H*W < 2^24 and W <= 1024 (pmt_warp1d_rows_supported() == 1) the taps of a pixel stay in its image
+ *   row and the backward is a deterministic per-row gather (CSR of the taps built once per row in shared
+ *   memory): bit-reproducible, no atomics.  Otherwise it zeroes gimg and scatters with fp32 atomics like the
+ *   reference's gather backward.
  *   goff[n,0,h,w] = sum_c gout*(img[x1]-img[x0]) where 0 <= w+off <= W-1, else 0.
- *   `gout` uses the same storage order flag as `out`.
+ *   `gout` uses the same storage order flag as `out`.  gimg or goff may be NULL (not both).
  * ------------------------------------------------------------------------------------------- */
 int pmt_warp1d_fwd_f32(const float* img, const float* off, float* out, int N, int C, int H, int W,
                        int out_cnhw, void* stream);
 int pmt_warp1d_bwd_f32(const float* img, const float* off, const float* gout, float* gimg,
                        float* goff, int N, int C, int H, int W, int gout_cnhw, void* stream);
+int pmt_warp1d_rows_supported(int N, int H, int W);
+
+/* f4 (next row): the warp fused with its two consumers.  All tensors (N,C,H,W) / (N,1,H,W)
+ * dense NCHW.
+ *   blend -- models/dsnet_t2_warp.py:697-698:  warped = apply_disparity(img, off);
+ *            out = (1 - att) * seg + att * warped  (the reference's three rounded fp32 steps: bit-identical).
+ *            `warped` (may be NULL) receives the warped tensor the model returns as well.
+ *            backward: gout = d/d out, gwarped = d/d warped (may be NULL);
+ *              gseg = (1-att)*gout;  gatt = sum_c gout*(warped - seg);  gimg/goff = warp backward of att*gout + gwarped.
+ *   photo-consistency MSE -- torch_implementation.py:314-317 with warped_right = apply_disparity(right, -disp)
+ *            [* (disp > 0) when mask_positive_disp, models/dsnet_t2_warp.py:811]:
+ *            loss = mean((warped*mask - left)^2), reduced in a fixed order (bit-reproducible).  `workspace` holds
+ *            pmt_warp1d_mse_workspace() doubles.  backward: gloss = device scalar d/d loss (NULL = 1);
+ *            gleft = -2*gloss/numel*(warped*mask - left); gimg/goff = warp backward of mask * (-gleft).
+ * The backward entry points need pmt_warp1d_rows_supported(N,H,W) == 1. */
+int pmt_warp1d_blend_fwd_f32(const float* img, const float* off, const float* att, const float* seg, float* out,
+                             float* warped, int N, int C, int H, int W, void* stream);
+int pmt_warp1d_blend_bwd_f32(const float* img, const float* off, const float* att, const float* seg, const float* gout,
+                             const float* gwarped, float* gimg, float* goff, float* gatt, float* gseg, int N, int C,
+                             int H, int W, void* stream);
+int pmt_warp1d_mse_workspace(void);
+int pmt_warp1d_mse_fwd_f32(const float* img, const float* off, const float* left, int mask_positive_disp,
+                           double* workspace, float* loss, int N, int C, int H, int W, void* stream);
+int pmt_warp1d_mse_bwd_f32(const float* img, const float* off, const float* left, int mask_positive_disp,
+                           const float* gloss, float* gimg, float* goff, float* gleft, int N, int C, int H, int W,
+                           void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * f4 (next row): SyncBatchNorm for a siamese pair fed as ONE batch x = [left; right] (2B,C,H,W).

@@ -62,10 +62,53 @@ def _reference_volume_loop(ref_fea, tgt_fea, maxdisp):
     return ns["cost"]
 
 
+def make_warp_fused(apply_disparity):
+    """f4 fixtures: the reference's own warp + the two consumer expressions, gradients by autograd through them.
+      blend: models/dsnet_t2_warp.py:697-698      seg_branch_right = apply_disparity(seg_branch_right, -disp_out)
+                                                  seg_branch_both = (1 - at_d) * seg_branch + at_d * seg_branch_right
+      photo: torch_implementation.py:314-317      nn.MSELoss()(warped_right, left), warped_right = apply_disparity(right, -disp)
+             [* (disp > 0)], models/dsnet_t2_warp.py:811"""
+    g = torch.Generator().manual_seed(4321)
+    N, C, H, W = 2, 3, 4, 24
+    seg = torch.randn(N, C, H, W, generator=g).requires_grad_(True)
+    seg_r = torch.randn(N, C, H, W, generator=g).requires_grad_(True)
+    disp = (torch.rand(N, 1, H, W, generator=g) * 14.0 - 3.0)
+    disp[0, 0, 0, :] = 0.0
+    disp[1, 0, 1, :] = torch.arange(W).float()          # lands exactly on x = 0
+    disp.requires_grad_(True)
+    at = torch.rand(N, 1, H, W, generator=g).requires_grad_(True)
+    warped = apply_disparity(seg_r, -disp, tensor_type="torch.FloatTensor")
+    both = (1 - at) * seg + at * warped
+    gboth = torch.randn(both.shape, generator=g)
+    gwarped = torch.randn(warped.shape, generator=g)
+    gs, gr, gd, ga = torch.autograd.grad((both, warped), (seg, seg_r, disp, at), (gboth, gwarped))
+    blob = {"seg": seg.detach().numpy(), "seg_r": seg_r.detach().numpy(), "disp": disp.detach().numpy(),
+            "att": at.detach().numpy(), "both": both.detach().contiguous().numpy(),
+            "warped": warped.detach().contiguous().numpy(), "gboth": gboth.numpy(), "gwarped": gwarped.contiguous().numpy(),
+            "gseg": gs.numpy(), "gseg_r": gr.numpy(), "gdisp": gd.numpy(), "gatt": ga.numpy()}
+    left = torch.rand(N, C, H, W, generator=g).requires_grad_(True)
+    right = torch.rand(N, C, H, W, generator=g).requires_grad_(True)
+    for name, mask in (("plain", False), ("masked", True)):
+        d = disp.detach().clone().requires_grad_(True)
+        wr = apply_disparity(right, -d, tensor_type="torch.FloatTensor")
+        if mask:
+            wr = wr * (d > 0)
+        loss = torch.nn.MSELoss()(wr, left)
+        gl, grr, gdd = torch.autograd.grad(3.0 * loss, (left, right, d))     # upstream gradient 3.0
+        blob.update({f"mse_{name}_loss": loss.detach().numpy(), f"mse_{name}_gleft": gl.numpy(),
+                     f"mse_{name}_gright": grr.numpy(), f"mse_{name}_gdisp": gdd.numpy()})
+    blob.update({"left": left.detach().numpy(), "right": right.detach().numpy()})
+    np.savez(os.path.join(OUT, "warp_fused_small.npz"), **blob)
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     apply_disparity, disparityregression, matchshifted = _load_reference()
     from oracle import torch_ref
+    if "--only-warp-fused" in sys.argv:      # added in round 2: leaves the round-1 fixtures byte-identical
+        make_warp_fused(apply_disparity)
+        print("wrote warp_fused_small.npz")
+        return
     g = torch.Generator().manual_seed(1234)
 
     # ---- a4 warp ------------------------------------------------------------------------------
@@ -153,6 +196,7 @@ def main():
     (gc3,) = torch.autograd.grad(pred, cost3, gp)
     np.savez(os.path.join(OUT, "upsoftargmin_small.npz"), cost3=cost3.detach().numpy(), pred=pred.detach().numpy(),
              gpred=gp.numpy(), gcost3=gc3.numpy(), maxdisp=np.array(maxdisp), size=np.array([H, W]))
+    make_warp_fused(apply_disparity)
     print("wrote", sorted(os.listdir(OUT)))
 
 

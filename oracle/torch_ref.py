@@ -85,3 +85,18 @@ def warp_ref(img: torch.Tensor, off: torch.Tensor) -> torch.Tensor:
     pl = torch.gather(img, 3, il)
     pr = torch.gather(img, 3, ir)
     return (x1 - x) * pl + (x - x0) * pr
+
+
+def warp_blend_ref(seg_left, seg_right, off, att):
+    """models/dsnet_t2_warp.py:697-698: (1 - at_d) * seg_branch + at_d * apply_disparity(seg_branch_right, off)."""
+    warped = warp_ref(seg_right, off)
+    return (1 - att) * seg_left + att * warped, warped
+
+
+def photo_mse_ref(right, off, left, mask_positive_disparity=False):
+    """torch_implementation.py:314-317 with warped_right = apply_disparity(right, off) [* (disp > 0), disp = -off,
+    models/dsnet_t2_warp.py:811]."""
+    wr = warp_ref(right, off)
+    if mask_positive_disparity:
+        wr = wr * (off < 0)
+    return F.mse_loss(wr, left)

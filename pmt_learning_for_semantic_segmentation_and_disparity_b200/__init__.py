@@ -9,7 +9,7 @@ from .correlation import (SpatialCorrelationSampler, SpatialCorrelationSamplerFu
                           get_correlation_engine, set_correlation_engine, spatial_correlation_sample)
 from .psmnet import (build_concat_volume, disparityregression, matchshifted, softargmin,  # noqa: F401
                      upsample_softargmin)
-from .warp import apply_disparity  # noqa: F401
+from .warp import apply_disparity, photo_consistency_mse, warp_blend  # noqa: F401
 from .syncbn import PairedSyncBatchNorm, pair_batchnorms  # noqa: F401
 from .compat import install_reference_shims  # noqa: F401
 

@@ -44,6 +44,12 @@ _SIGNATURES = {
     "pmt_bn_pair_bwd_apply_f32": [_P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _P, _I, _P],
     "pmt_warp1d_fwd_f32": [_P, _P, _P, _I, _I, _I, _I, _I, _P],
     "pmt_warp1d_bwd_f32": [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P],
+    "pmt_warp1d_rows_supported": [_I, _I, _I],
+    "pmt_warp1d_blend_fwd_f32": [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _P],
+    "pmt_warp1d_blend_bwd_f32": [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _P],
+    "pmt_warp1d_mse_workspace": [],
+    "pmt_warp1d_mse_fwd_f32": [_P, _P, _P, _I, _P, _P, _I, _I, _I, _I, _P],
+    "pmt_warp1d_mse_bwd_f32": [_P, _P, _P, _I, _P, _P, _P, _P, _I, _I, _I, _I, _P],
     "pmt_corr1d_fwd_bwd_host_f32": [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I],
     "pmt_probe_fp32_fma": [_I, ctypes.POINTER(ctypes.c_double), _P],
     "pmt_probe_copy": [_P, _P, ctypes.c_int64, ctypes.POINTER(ctypes.c_double), _P],

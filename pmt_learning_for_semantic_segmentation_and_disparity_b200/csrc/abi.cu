@@ -27,6 +27,9 @@ int launch_corr1d_fwd_tc(const float*, const float*, float*, int, int, int, int,
 bool corr1d_bwd_tc_ok(const void*, const void*, int C, int H, int W, int P, int dilp, int passes);
 int launch_corr1d_bwd_tc(const float*, const float*, const float*, float*, float*, int, int, int, int, int, int,
                          cudaStream_t);
+bool corr1d_bwd_tca_ok(const void*, const void*, int C, int H, int W, int P, int dilp, int passes);
+int launch_corr1d_bwd_tca(const float*, const float*, const float*, float*, float*, int, int, int, int, int, int,
+                          cudaStream_t);
 int launch_concat_fwd(const float*, const float*, float*, int, int, int, int, int, int, cudaStream_t);
 int launch_concat_bwd(const float*, float*, float*, int, int, int, int, int, int, cudaStream_t);
 int launch_softargmin_fwd(const float*, float*, float*, int, int, int, int, cudaStream_t);
@@ -48,6 +51,16 @@ int launch_bn_pair_bwd_apply(const float*, const float*, const float*, const flo
 int launch_warp_fwd(const float*, const float*, float*, int, int, int, int, int, cudaStream_t);
 int launch_warp_bwd(const float*, const float*, const float*, float*, float*, int, int, int, int, int,
                     cudaStream_t);
+
+bool warp_rows_supported(int, int, int);
+int launch_warp_blend_fwd(const float*, const float*, const float*, const float*, float*, float*, int, int, int, int,
+                          cudaStream_t);
+int launch_warp_blend_bwd(const float*, const float*, const float*, const float*, const float*, const float*, float*, float*,
+                          float*, float*, int, int, int, int, cudaStream_t);
+int warp_mse_workspace();
+int launch_warp_mse_fwd(const float*, const float*, const float*, int, double*, float*, int, int, int, int, cudaStream_t);
+int launch_warp_mse_bwd(const float*, const float*, const float*, int, const float*, float*, float*, float*, int, int, int, int,
+                        cudaStream_t);
 
 extern long long* g_bwd_prof;  // corr1d_bwd_tc.cu (profiling builds)
 
@@ -198,7 +211,9 @@ static int check_corr_args(const void* a, const void* b, const void* c, int B, i
 
 int pmt_corr1d_uses_fast_path(const void* in1, const void* in2, const void* third, int C, int H, int W,
                               int P, int dilp) {
-  if (corr1d_fwd_tc_ok(in1, in2, third, C, H, W, P, dilp, 3) && corr1d_bwd_tc_ok(in1, in2, C, H, W, P, dilp, 3)) return 2;
+  if (corr1d_fwd_tc_ok(in1, in2, third, C, H, W, P, dilp, 3) &&
+      (corr1d_bwd_tca_ok(in1, in2, C, H, W, P, dilp, 3) || corr1d_bwd_tc_ok(in1, in2, C, H, W, P, dilp, 3)))
+    return 2;
   return (corr1d_fwd_fast_ok(in1, in2, W, P, dilp) && corr1d_bwd_fast_ok(in1, in2, third, C, W, P, dilp)) ? 1 : 0;
 }
 
@@ -240,8 +255,12 @@ int pmt_corr1d_bwd_f32(const float* in1, const float* in2, const float* gout, fl
   if (int e = check_corr_args(in1, in2, gout, B, C, H, W, 1, P, 1, dilp)) return e;
   PMT_CHECK_ARG(gin1 && gin2, "correlation backward: null gradient pointer");
   if ((int64_t)B * C * H * W == 0) return PMT_OK;
-  if (corr1d_bwd_tc_ok(in1, in2, C, H, W, P, dilp, 3) && aligned16(gout))
-    return launch_corr1d_bwd_tc(in1, in2, gout, gin1, gin2, B, C, H, W, P, 3, static_cast<cudaStream_t>(stream));
+  if (aligned16(gout) && aligned16(gin1) && aligned16(gin2)) {
+    if (PMT_ENV_INT("PMT_BWD_V1", 0) == 0 && corr1d_bwd_tca_ok(in1, in2, C, H, W, P, dilp, 3))
+      return launch_corr1d_bwd_tca(in1, in2, gout, gin1, gin2, B, C, H, W, P, 3, static_cast<cudaStream_t>(stream));
+    if (corr1d_bwd_tc_ok(in1, in2, C, H, W, P, dilp, 3))
+      return launch_corr1d_bwd_tc(in1, in2, gout, gin1, gin2, B, C, H, W, P, 3, static_cast<cudaStream_t>(stream));
+  }
   return pmt_corr1d_bwd_simt_f32(in1, in2, gout, gin1, gin2, B, C, H, W, P, dilp, stream);
 }
 
@@ -263,8 +282,10 @@ int pmt_corr1d_bwd_tc_f32(const float* in1, const float* in2, const float* gout,
   PMT_CHECK_ARG(gin1 && gin2, "correlation backward: null gradient pointer");
   PMT_CHECK_ARG(passes == 1 || passes == 3, "corr1d tc: passes must be 1 (tf32) or 3 (3xtf32)");
   if ((int64_t)B * C * H * W == 0) return PMT_OK;
+  if (PMT_ENV_INT("PMT_BWD_V1", 0) == 0 && corr1d_bwd_tca_ok(in1, in2, C, H, W, P, dilp, passes) && aligned16(gout))
+    return launch_corr1d_bwd_tca(in1, in2, gout, gin1, gin2, B, C, H, W, P, passes, static_cast<cudaStream_t>(stream));
   if (!corr1d_bwd_tc_ok(in1, in2, C, H, W, P, dilp, passes)) {
-    set_error("corr1d tc bwd: shape/alignment not supported by the tensor-core path (W%%4, 16-byte pointers, C<=128, dilp=1)");
+    set_error("corr1d tc bwd: shape/alignment not supported by the tensor-core path (W%%4, 16-byte pointers, P<=256, dilp=1)");
     return PMT_ERR_UNSUPPORTED;
   }
   return launch_corr1d_bwd_tc(in1, in2, gout, gin1, gin2, B, C, H, W, P, passes, static_cast<cudaStream_t>(stream));
@@ -393,6 +414,42 @@ int pmt_warp1d_bwd_f32(const float* img, const float* off, const float* gout, fl
   PMT_CHECK_ARG(gimg || goff, "warp backward: nothing to compute");
   PMT_CHECK_ARG(N >= 0 && C >= 0 && H >= 0 && W >= 0, "warp: negative dimension");
   return launch_warp_bwd(img, off, gout, gimg, goff, N, C, H, W, gout_cnhw, static_cast<cudaStream_t>(stream));
+}
+
+int pmt_warp1d_rows_supported(int N, int H, int W) { return warp_rows_supported(N, H, W) ? 1 : 0; }
+
+int pmt_warp1d_blend_fwd_f32(const float* img, const float* off, const float* att, const float* seg, float* out,
+                             float* warped, int N, int C, int H, int W, void* stream) {
+  PMT_CHECK_ARG(img && off && att && seg && out, "warp blend: null pointer");
+  PMT_CHECK_ARG(N >= 0 && C >= 0 && H >= 0 && W >= 0, "warp: negative dimension");
+  return launch_warp_blend_fwd(img, off, att, seg, out, warped, N, C, H, W, static_cast<cudaStream_t>(stream));
+}
+
+int pmt_warp1d_blend_bwd_f32(const float* img, const float* off, const float* att, const float* seg, const float* gout,
+                             const float* gwarped, float* gimg, float* goff, float* gatt, float* gseg, int N, int C, int H,
+                             int W, void* stream) {
+  PMT_CHECK_ARG(img && off && att && seg && gout && gimg && goff && gatt && gseg, "warp blend backward: null pointer");
+  PMT_CHECK_ARG(N >= 0 && C >= 0 && H >= 0 && W >= 0, "warp: negative dimension");
+  return launch_warp_blend_bwd(img, off, att, seg, gout, gwarped, gimg, goff, gatt, gseg, N, C, H, W,
+                               static_cast<cudaStream_t>(stream));
+}
+
+int pmt_warp1d_mse_workspace(void) { return warp_mse_workspace(); }
+
+int pmt_warp1d_mse_fwd_f32(const float* img, const float* off, const float* left, int mask_positive_disp, double* workspace,
+                           float* loss, int N, int C, int H, int W, void* stream) {
+  PMT_CHECK_ARG(img && off && left && workspace && loss, "warp photo-consistency: null pointer");
+  PMT_CHECK_ARG(N >= 0 && C >= 0 && H >= 0 && W >= 0, "warp: negative dimension");
+  return launch_warp_mse_fwd(img, off, left, mask_positive_disp, workspace, loss, N, C, H, W, static_cast<cudaStream_t>(stream));
+}
+
+int pmt_warp1d_mse_bwd_f32(const float* img, const float* off, const float* left, int mask_positive_disp, const float* gloss,
+                           float* gimg, float* goff, float* gleft, int N, int C, int H, int W, void* stream) {
+  PMT_CHECK_ARG(img && off && left, "warp photo-consistency backward: null pointer");
+  PMT_CHECK_ARG(gimg || goff || gleft, "warp photo-consistency backward: nothing to compute");
+  PMT_CHECK_ARG(N >= 0 && C >= 0 && H >= 0 && W >= 0, "warp: negative dimension");
+  return launch_warp_mse_bwd(img, off, left, mask_positive_disp, gloss, gimg, goff, gleft, N, C, H, W,
+                             static_cast<cudaStream_t>(stream));
 }
 
 // Host-buffer forward+backward of the 1 x P correlation.  Batch items flow through kSlots device slots; each slot

@@ -29,6 +29,20 @@ __device__ __forceinline__ void fence_after_sync() {
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 }
 
+// One lane of a converged warp (elect.sync).  The MMA-issuing warp runs its loop with all 32 lanes converged and issues
+// under `if (elect_one())`: the compiler then keeps descriptors and ring counters in uniform registers and emits
+// straight-line UTCHMMA, instead of the per-thread registers + R2UR moves + ELECT/BRA.U.ANY serialisation loop it
+// generates for a loop that runs under `if (lane == 0)`.
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
+
 // ---- descriptors -----------------------------------------------------------------------------
 // Shared-memory matrix descriptor, Blackwell version bit set.
 //   bits [0,14) start>>4 | [16,30) LBO>>4 | [32,46) SBO>>4 | [46,48) version=1 | [61,64) layout (2 = SW128)

@@ -35,6 +35,9 @@ if mode == "small":
     run(1, 40, 3, 132, 40, 3)
     run(1, 128, 4, 64, 17, 3)
     run(1, 5, 3, 100, 8, 3)
+    run(2, 352, 32, 64, 17, 3)      # production call of minidsnetExt: three channel blocks
+    run(1, 130, 5, 260, 193, 3)     # 2 channel blocks, P > 192, ragged W
+    run(1, 96, 4, 256, 100, 1)
 else:
     run(4, 64, 256, 512, 192, 1, iters=20)
     run(4, 64, 256, 512, 192, 3, iters=20)

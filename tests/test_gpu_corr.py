@@ -36,7 +36,8 @@ def run_corr(pmt, L, R, G, patch, dil=1):
 # (B, C, H, W, P, engine the default entry points pick: 2 tensor core, 1 CUDA-core tiled, 0 generic)
 CORR1D_CASES = [
     (2, 64, 64, 128, 40, 2),     # BASELINE config 1
-    (2, 352, 32, 64, 17, 1),     # production call inside minidsnetExt (C > 128: CUDA-core tiled backward)
+    (2, 352, 32, 64, 17, 2),     # production call inside minidsnetExt (C > 128: three channel blocks on the tensor cores)
+    (1, 130, 2, 260, 33, 2),     # two channel blocks, the second with 2 live channels; W%128 != 0
     (1, 64, 5, 512, 192, 2),     # headline row shape
     (1, 16, 3, 512, 193, 2),     # largest P of the fast paths
     (1, 5, 3, 100, 8, 2),        # ragged: W%64 != 0, C%16 != 0, even P

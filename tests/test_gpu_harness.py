@@ -44,7 +44,10 @@ def test_paired_batchnorm_equals_two_calls_fp64():
 
     ref, par = tower(), tower()
     par.load_state_dict(ref.state_dict())
-    harness.pair_batchnorms(par)
+    harness.pair_batchnorms(par, fuse_relu=True)
+    for m in par.modules():
+        if isinstance(m, harness.PairedSyncBatchNorm):
+            m.fused = False        # float64 reference path (the kernels are fp32-only and refuse anything else)
     assert isinstance(par[1], harness.PairedSyncBatchNorm) and isinstance(par[4], harness.PairedSyncBatchNorm)
     assert par[1].relu and isinstance(par[2], torch.nn.Identity) and not par[4].relu   # the ReLU moved into the BN
     left = torch.rand(3, 3, 20, 28, device=DEV, dtype=torch.float64)

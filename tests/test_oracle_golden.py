@@ -9,6 +9,8 @@ import torch
 import oracle
 from oracle import torch_ref
 
+FP32_TOL = 1e-5
+
 
 def rel_err(a, b):
     a = np.asarray(a, dtype=np.float64)
@@ -163,3 +165,28 @@ def test_upsample_softargmin_bwd_oracle_vs_reference_autograd(golden_dir):
     assert g.shape == d["gcost3"].shape
     assert rel_err(g, d["gcost3"]) <= 1e-5
 
+
+
+def test_warp_fused_torch_ref_matches_reference(golden_dir):
+    """f4: the oracle's blend / photo-consistency restatements against fixtures produced by the reference's own
+    apply_disparity + its blend expression / nn.MSELoss, gradients by autograd (oracle/make_golden.py::make_warp_fused)."""
+    import torch
+
+    from oracle import torch_ref
+
+    d = np.load(os.path.join(golden_dir, "warp_fused_small.npz"))
+    t = lambda k: torch.from_numpy(d[k]).requires_grad_(True)
+    seg, seg_r, disp, att = t("seg"), t("seg_r"), t("disp"), t("att")
+    both, warped = torch_ref.warp_blend_ref(seg, seg_r, -disp, att)
+    assert np.array_equal(both.detach().numpy(), d["both"]) and np.array_equal(warped.detach().numpy(), d["warped"])
+    gs, gr, gd, ga = torch.autograd.grad((both, warped), (seg, seg_r, disp, att),
+                                         (torch.from_numpy(d["gboth"]), torch.from_numpy(d["gwarped"])))
+    for got, key in ((gs, "gseg"), (gr, "gseg_r"), (gd, "gdisp"), (ga, "gatt")):
+        assert rel_err(got.numpy(), d[key]) <= FP32_TOL, key
+    for name, mask in (("plain", False), ("masked", True)):
+        left, right, dd = t("left"), t("right"), t("disp")
+        loss = torch_ref.photo_mse_ref(right, -dd, left, mask)
+        assert abs(float(loss) - float(d[f"mse_{name}_loss"])) <= 1e-6 * float(d[f"mse_{name}_loss"])
+        gl, grr, gdd = torch.autograd.grad(3.0 * loss, (left, right, dd))
+        for got, key in ((gl, "gleft"), (grr, "gright"), (gdd, "gdisp")):
+            assert rel_err(got.numpy(), d[f"mse_{name}_{key}"]) <= FP32_TOL, (name, key)
