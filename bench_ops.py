@@ -99,6 +99,41 @@ def run_ops(iters: int = 50, device_index: int = 0, emit=None, quick: bool = Fal
         del S
         torch.cuda.empty_cache()
 
+    # ---- f3: 2-D (17,17) patch of `-corrType 2dcorr` at the production feature shape; f2: corr + corrConv2d + ReLU ----
+    B, C, H, W = 4, 352, 32, 64
+    a2, b2 = torch.randn(B, C, H, W, device=dev), torch.randn(B, C, H, W, device=dev)
+    o2 = torch.empty(B, 17, 17, H, W, device=dev)
+    g2 = torch.randn(B, 17, 17, H, W, device=dev)
+    ga2, gb2 = torch.empty_like(a2), torch.empty_like(b2)
+    ms = timed(lambda i: lib.pmt_corr_fwd_f32(vp(a2), vp(b2), vp(o2), B, C, H, W, 17, 17, 1, 1, sp), 1)
+    report("corr2d_fwd (17,17)", "2dcorr C=352 32x64 B=4", ms, 4 * (2 * B * C * H * W + o2.numel()), B,
+           {"useful_tflops": 2.0 * B * C * H * W * 289 / (ms * 1e-3) * 1e-12})
+    ms = timed(lambda i: lib.pmt_corr_bwd_f32(vp(a2), vp(b2), vp(g2), vp(ga2), vp(gb2), B, C, H, W, 17, 17, 1, 1, sp), 1)
+    report("corr2d_bwd (17,17)", "2dcorr C=352 32x64 B=4", ms, 4 * (4 * B * C * H * W + o2.numel()), B,
+           {"useful_tflops": 4.0 * B * C * H * W * 289 / (ms * 1e-3) * 1e-12})
+    wt = torch.randn(128, 17, device=dev) * 0.1
+    z = torch.empty(B, 128, H, W, device=dev)
+    cs = torch.empty(B, 17, H, W, device=dev)
+    gz = torch.randn(B, 128, H, W, device=dev)
+    gw, work = torch.empty(128, 17, device=dev), torch.empty(B * H, 128 * 17, device=dev)
+    ms = timed(lambda i: lib.pmt_corr1d_conv_relu_fwd_f32(vp(a2), vp(b2), vp(wt), vp(z), vp(cs), B, C, H, W, 17, 128, sp), 1)
+    report("corr1d+conv1x1+relu fwd (fused f2)", "production C=352 32x64 P=17 O=128 B=4", ms, 4 * (2 * B * C * H * W + z.numel()), B)
+    ms = timed(lambda i: lib.pmt_corr1d_conv_relu_bwd_f32(vp(a2), vp(b2), vp(wt), vp(z), vp(cs), vp(gz), vp(ga2), vp(gb2), vp(gw),
+                                                          vp(work), B, C, H, W, 17, 128, sp), 1)
+    report("corr1d+conv1x1+relu bwd (fused f2)", "production", ms, 4 * (4 * B * C * H * W + 2 * z.numel()), B)
+    if not quick:
+        conv = torch.nn.Sequential(torch.nn.Conv2d(17, 128, 1, bias=False), torch.nn.ReLU(inplace=True)).to(dev)
+        smp = pmt.SpatialCorrelationSampler(kernel_size=1, patch_size=(1, 17), stride=1, padding=0, dilation_patch=1)
+        ar, br = a2.clone().requires_grad_(True), b2.clone().requires_grad_(True)
+
+        def unfused_f2(i):
+            ar.grad = br.grad = None
+            conv(torch.squeeze(smp(ar, br), 1)).backward(gz)
+
+        ms = timed(unfused_f2, 1)
+        report("sampler -> conv2d -> relu fwd+bwd [unfused: our sampler + cuDNN]", "production", ms, 0, B)
+    del a2, b2, o2, g2, ga2, gb2
+
     # ---- PSMNet ops (config 3: B=4, 32ch 64x128 -> (64,48,64,128); cost (4,192,256,512)) ---------------
     B, C, D, H, W = 4, 32, 48, 64, 128
     ref = [torch.randn(B, C, H, W, device=dev) for _ in range(2)]
@@ -174,11 +209,19 @@ def run_ops(iters: int = 50, device_index: int = 0, emit=None, quick: bool = Fal
         report("warp1d_fwd", f"N={N} C={C} {H}x{W}", ms, 4 * N * H * W * (2 * C + 1), N)
 
         def wb(i):
-            gi.zero_()
             return lib.pmt_warp1d_bwd_f32(vp(img), vp(off), vp(g), vp(gi), vp(gof), N, C, H, W, 1, sp)
 
         ms = timed(wb, 1)
-        report("warp1d_bwd (+zero fill of gimg)", f"N={N} C={C} {H}x{W}", ms, 4 * N * H * W * (3 * C + 2), N)
+        report("warp1d_bwd (deterministic row gather)", f"N={N} C={C} {H}x{W}", ms, 4 * N * H * W * (3 * C + 2), N)
+        if C <= 3:
+            seg, att = torch.randn(N, C, H, W, device=dev), torch.rand(N, 1, H, W, device=dev)
+            ob, ow = torch.empty(N, C, H, W, device=dev), torch.empty(N, C, H, W, device=dev)
+            gb_, gs_, ga_ = torch.randn(N, C, H, W, device=dev), torch.empty(N, C, H, W, device=dev), torch.empty_like(att)
+            ms = timed(lambda i: lib.pmt_warp1d_blend_fwd_f32(vp(img), vp(off), vp(att), vp(seg), vp(ob), vp(ow), N, C, H, W, sp), 1)
+            report("warp+blend fwd (fused f4)", f"N={N} C={C} {H}x{W}", ms, 4 * N * H * W * (4 * C + 2), N)
+            ms = timed(lambda i: lib.pmt_warp1d_blend_bwd_f32(vp(img), vp(off), vp(att), vp(seg), vp(gb_), None, vp(gi), vp(gof),
+                                                              vp(ga_), vp(gs_), N, C, H, W, sp), 1)
+            report("warp+blend bwd (fused f4)", f"N={N} C={C} {H}x{W}", ms, 4 * N * H * W * (5 * C + 4), N)
 
     return lines
 

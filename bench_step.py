@@ -35,6 +35,12 @@ def main():
                     help="run the siamese tower twice (one SyncBatchNorm collective per call) instead of once over "
                          "[left; right] with per-half statistics and one collective per layer")
     ap.add_argument("--json-out", default="", help="also write the JSON record to this file (rank 0)")
+    ap.add_argument("--nccl-bn", action="store_true", help="exchange the BN statistics with NCCL collectives (one all_gather / "
+                                                           "all_reduce launch per layer and direction) instead of the "
+                                                           "NVLink peer-memory exchange inside the bn_pair kernels")
+    ap.add_argument("--full-depth", action="store_true", help="whole DenseNet-121 per image (121 BN layers per tower pass)")
+    ap.add_argument("--unfused", action="store_true", help="sampler -> conv -> relu and warp -> blend as separate ops")
+    ap.add_argument("--no-lovasz", action="store_true", help="drop the Lovasz-Softmax term of the seg2 loss")
     ap.add_argument("--graph", action="store_true", help="(default) capture the whole step, NCCL collectives included, "
                                                          "in one CUDA graph")
     args = ap.parse_args()
@@ -50,8 +56,12 @@ def main():
     dev = torch.device("cuda", world.local_rank)
     torch.cuda.set_device(dev)
     use_graph = not args.eager
+    paired = not args.no_pair and not args.no_sync_bn
+    peer = paired and not args.nccl_bn and world.distributed
     step, model = harness.build_training_step(world, batch_per_gpu=args.batch, sync_bn=not args.no_sync_bn,
-                                               cuda_graph=use_graph, paired_tower=not args.no_pair)
+                                               cuda_graph=use_graph, paired_tower=not args.no_pair, peer_bn=peer,
+                                               full_depth=args.full_depth, fused_ops=not args.unfused,
+                                               lovasz=not args.no_lovasz)
     for _ in range(max(args.warmup, 3)):
         loss = step()
     torch.cuda.synchronize(dev)
@@ -67,16 +77,24 @@ def main():
     value, ms = sharding.throughput(world, args.batch * args.steps, e0.elapsed_time(e1))
     if world.is_main:
         n_params = sum(p.numel() for p in model.parameters())
+        n_bn_paired = sum(isinstance(m, harness.PairedSyncBatchNorm) for m in model.modules())
+        n_bn_sync = sum(isinstance(m, torch.nn.SyncBatchNorm) for m in model.modules())
         rec = {"metric": "SDNetLite training step pairs/s (256x512, batch 4/GPU, DDP+SyncBN)", "value": value,
                "unit": "pairs/s", "n_gpus": world.world_size, "steps": args.steps,
                "ms_per_step": ms / args.steps, "scaling": "weak", "global_batch": args.batch * world.world_size,
                "params": n_params, "loss": float(loss.detach()), "sync_bn": not args.no_sync_bn,
-               "cuda_graph": use_graph, "paired_tower": not args.no_pair and not args.no_sync_bn,
-               "collectives": "DDP gradient all-reduce + SyncBatchNorm statistics (NCCL); none in the hot-path ops"}
+               "cuda_graph": use_graph, "paired_tower": paired, "bn_exchange": "nvlink-peer" if peer else "nccl",
+               "full_depth": args.full_depth, "fused_ops": not args.unfused, "lovasz": not args.no_lovasz,
+               "bn_layers_paired": n_bn_paired, "bn_layers_sync": n_bn_sync,
+               "nccl_launches_per_step_bn": (0 if peer else 2 * n_bn_paired) + 2 * n_bn_sync if world.distributed else 0,
+               "collectives": "DDP gradient all-reduce (NCCL); BN statistics: " +
+                              ("NVLink peer-memory exchange inside the bn_pair kernels" if peer else "NCCL all_gather / all_reduce")}
         print(json.dumps(rec), flush=True)
         if args.json_out:
             with open(args.json_out, "w") as f:
                 json.dump(rec, f)
+    if getattr(step, "exchange", None) is not None:
+        step.exchange.check()      # a kernel that gave up waiting for a peer would have produced garbage
     if use_graph and world.distributed:
         # A CUDA graph that holds captured NCCL kernels keeps the communicator busy: destroy_process_group() was
         # observed to block forever behind it (that -- not the capture -- was the "hang" of the first attempts).

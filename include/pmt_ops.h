@@ -75,6 +75,21 @@ int pmt_corr_fwd_f32(const float* in1, const float* in2, float* out, int B, int 
 int pmt_corr_bwd_f32(const float* in1, const float* in2, const float* gout, float* gin1,
                      float* gin2, int B, int C, int H, int W, int patchH, int patchW, int dilpH,
                      int dilpW, void* stream);
+/* f2 (next row): the 1 x P correlation fused with its epilogue
+ *     y = squeeze(correlation_sampler(a, b), 1); y = corrConv2d(y)        models/dsnet_t2.py:1187-1197, :879-888
+ *     corrConv2d = conv2dSame(P, O, 1, 'same') [bias=False] + ReLU        models/dsnet_t2.py:852, dsnet_t2_warp.py:664-671
+ *   z[n,o,h,w] = relu(sum_p weight[o,p] * sum_c in1[n,c,h,w]*in2[n,c,h,w+s_p]);  weight is (O,P) (= Conv2d weight
+ *   (O,P,1,1)); corr_save (B,P,H,W) receives the correlation slab (needed by the backward for gweight).
+ *   Backward: gin1, gin2, gweight (O,P) from gz = d/dz; workspace holds B*H*O*P floats (per-row partials of gweight,
+ *   reduced in fixed order: deterministic).  One CTA per image row; covers the production shape of the training
+ *   configurations (C=352, 32x64, P=17, O=128): pmt_corr1d_conv_relu_supported() tells (P==17, 16<=W<=128, W%4==0,
+ *   O<=256); other shapes return PMT_ERR_UNSUPPORTED (callers keep the unfused sampler -> conv -> relu sequence). */
+int pmt_corr1d_conv_relu_supported(int C, int H, int W, int P, int O);
+int pmt_corr1d_conv_relu_fwd_f32(const float* in1, const float* in2, const float* weight, float* z, float* corr_save,
+                                 int B, int C, int H, int W, int P, int O, void* stream);
+int pmt_corr1d_conv_relu_bwd_f32(const float* in1, const float* in2, const float* weight, const float* z,
+                                 const float* corr_save, const float* gz, float* gin1, float* gin2, float* gweight,
+                                 float* workspace, int B, int C, int H, int W, int P, int O, void* stream);
 /* which engine pmt_corr1d_{fwd,bwd}_f32 would use: 2 = tensor core (3xTF32), 1 = CUDA-core tiled, 0 = generic */
 int pmt_corr1d_uses_fast_path(const void* in1, const void* in2, const void* out_or_gout, int C,
                               int H, int W, int P, int dilp);
@@ -197,6 +212,35 @@ int pmt_bn_pair_bwd_reduce_f32(const float* dy, const float* x, const float* sav
 int pmt_bn_pair_bwd_apply_f32(const float* dy, const float* x, const float* save_mean, const float* save_invstd,
                               const float* weight, const float* sums, float* dx, int B, int C, int HW,
                               const float* bias, int relu, void* stream);
+
+/* The same four steps with the cross-rank exchange done BY THE KERNELS over NVLink peer memory instead of a collective
+ * between them (north_star: NCCL only for the gradient all-reduce; the statistics of a layer are 4C+1 floats and a
+ * collective launch per layer and direction is what limited the 8-GPU step).  Every rank owns a symmetric buffer of the
+ * same layout, mapped into every peer (torch.distributed._symmetric_memory / cudaIpc); `peer_bufs` is a DEVICE array of
+ * the `world` base pointers, `local_buf` this rank's own.  Per layer and direction the caller reserves, at float
+ * offsets that are equal on all ranks, a payload region [2][world][n] (n = 4C+1 forward, 4C backward) and a flag
+ * region [2][world] (int32, zero-initialised), plus LOCAL device words `epoch` (int, zero-initialised), `done`
+ * (unsigned, zero-initialised) and a shared `err` word (set to 1 if a wait exceeded ~2 s).
+ *   *_stats_peer / *_bwd_reduce_peer: compute, push the payload into slot [epoch parity][rank] of every peer, publish
+ *       the new epoch to every peer's flag (st.release.sys) from the last block;
+ *   *_apply_peer / *_bwd_apply_peer: wait (ld.acquire.sys) until all `world` flags show the local epoch, then read
+ *       the payloads from local_buf (backward: summed in rank order -> bit-identical on all ranks).
+ * Epochs advance on the device, so the sequence can be captured in a CUDA graph and replayed. */
+int pmt_bn_pair_stats_peer_f32(const float* x, void* const* peer_bufs, void* local_buf, int world, int rank,
+                               int64_t payload_off, int64_t flag_off, int* epoch, unsigned* done, int* err, int B, int C,
+                               int HW, void* stream);
+int pmt_bn_pair_apply_peer_f32(const float* x, void* local_buf, int world, int64_t payload_off, int64_t flag_off,
+                               int* epoch, int* err, const float* weight, const float* bias, float* running_mean,
+                               float* running_var, float momentum, float eps, float* out, float* save_mean,
+                               float* save_invstd, int B, int C, int HW, int relu, void* stream);
+int pmt_bn_pair_bwd_reduce_peer_f32(const float* dy, const float* x, const float* save_mean, const float* save_invstd,
+                                    void* const* peer_bufs, void* local_buf, int world, int rank, int64_t payload_off,
+                                    int64_t flag_off, int* epoch, unsigned* done, int* err, float* gw, float* gb, int B,
+                                    int C, int HW, const float* weight, const float* bias, int relu, void* stream);
+int pmt_bn_pair_bwd_apply_peer_f32(const float* dy, const float* x, const float* save_mean, const float* save_invstd,
+                                   const float* weight, void* local_buf, int world, int64_t payload_off,
+                                   int64_t flag_off, int* epoch, int* err, float* dx, int B, int C, int HW,
+                                   const float* bias, int relu, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Host-buffer entry point for the headline workload (what a non-PyTorch caller of the reference's

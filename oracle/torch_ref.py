@@ -100,3 +100,10 @@ def photo_mse_ref(right, off, left, mask_positive_disparity=False):
     if mask_positive_disparity:
         wr = wr * (off < 0)
     return F.mse_loss(wr, left)
+
+
+def corr_conv_relu_ref(in1, in2, weight, patch_size=(1, 17)):
+    """models/dsnet_t2.py:1187-1197 for `1dcorr`: squeeze(correlation_sampler(a, b), 1) -> corrConv2d (bias-free 1x1
+    convolution, models/torch_model.py:236-272 with kernel 1 => no padding) -> ReLU."""
+    y = torch.squeeze(corr_ref(in1, in2, patch_size), dim=1)
+    return F.relu(F.conv2d(y, weight.view(weight.size(0), -1, 1, 1)))

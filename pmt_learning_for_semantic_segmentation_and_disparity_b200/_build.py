@@ -9,7 +9,7 @@ PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG_DIR, "csrc")
 INCLUDE = os.path.join(os.path.dirname(PKG_DIR), "include")
 LIB_PATH = os.path.join(PKG_DIR, "libpmt_ops.so")
-SOURCES = ["abi.cu", "corr_generic.cu", "corr1d_fwd.cu", "corr1d_bwd.cu", "corr1d_fwd_tc.cu", "corr1d_bwd_tc.cu", "corr1d_bwd_tca.cu", "psmnet_ops.cu", "warp1d.cu", "bn_pair.cu"]
+SOURCES = ["abi.cu", "corr_generic.cu", "corr1d_fwd.cu", "corr1d_bwd.cu", "corr1d_fwd_tc.cu", "corr1d_bwd_tc.cu", "corr1d_bwd_tca.cu", "corr_conv_fused.cu", "corr2d_rows.cu", "psmnet_ops.cu", "warp1d.cu", "bn_pair.cu"]
 
 
 def _nvcc() -> str:

@@ -17,6 +17,7 @@ _lock = threading.Lock()
 _I = ctypes.c_int
 _F = ctypes.c_float
 _P = ctypes.c_void_p
+_L = ctypes.c_int64
 
 # name -> argtypes (every function returns int unless listed in _SPECIAL)
 _SIGNATURES = {
@@ -42,8 +43,15 @@ _SIGNATURES = {
     "pmt_bn_pair_apply_f32": [_P, _P, _I, _P, _P, _P, _P, _F, _F, _P, _P, _P, _I, _I, _I, _I, _P],
     "pmt_bn_pair_bwd_reduce_f32": [_P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _P, _P, _I, _P],
     "pmt_bn_pair_bwd_apply_f32": [_P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _P, _I, _P],
+    "pmt_bn_pair_stats_peer_f32": [_P, _P, _P, _I, _I, _L, _L, _P, _P, _P, _I, _I, _I, _P],
+    "pmt_bn_pair_apply_peer_f32": [_P, _P, _I, _L, _L, _P, _P, _P, _P, _P, _P, _F, _F, _P, _P, _P, _I, _I, _I, _I, _P],
+    "pmt_bn_pair_bwd_reduce_peer_f32": [_P, _P, _P, _P, _P, _P, _I, _I, _L, _L, _P, _P, _P, _P, _P, _I, _I, _I, _P, _P, _I, _P],
+    "pmt_bn_pair_bwd_apply_peer_f32": [_P, _P, _P, _P, _P, _P, _I, _L, _L, _P, _P, _P, _I, _I, _I, _P, _I, _P],
     "pmt_warp1d_fwd_f32": [_P, _P, _P, _I, _I, _I, _I, _I, _P],
     "pmt_warp1d_bwd_f32": [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P],
+    "pmt_corr1d_conv_relu_supported": [_I, _I, _I, _I, _I],
+    "pmt_corr1d_conv_relu_fwd_f32": [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P],
+    "pmt_corr1d_conv_relu_bwd_f32": [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P],
     "pmt_warp1d_rows_supported": [_I, _I, _I],
     "pmt_warp1d_blend_fwd_f32": [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _P],
     "pmt_warp1d_blend_bwd_f32": [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _P],

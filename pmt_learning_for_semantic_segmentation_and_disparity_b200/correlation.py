@@ -135,3 +135,87 @@ class SpatialCorrelationSampler(nn.Module):
     def extra_repr(self):
         return (f"kernel_size={self.kernel_size}, patch_size={self.patch_size}, stride={self.stride}, "
                 f"padding={self.padding}, dilation={self.dilation}, dilation_patch={self.dilation_patch}")
+
+
+class _CorrConvReLU(Function):
+    @staticmethod
+    def forward(ctx, input1, input2, weight, patch):
+        in1 = U.require_cuda_f32(input1, "input1")
+        in2 = U.require_cuda_f32(input2, "input2")
+        wt = U.require_cuda_f32(weight, "weight")
+        if in1.dim() != 4 or in1.shape != in2.shape:
+            raise ValueError(f"input1/input2 must be 4-D (B,C,H,W) of equal shape, got {tuple(input1.shape)} and "
+                             f"{tuple(input2.shape)}")
+        B, C, H, W = in1.shape
+        O = wt.size(0)
+        if wt.numel() != O * patch:
+            raise ValueError(f"weight must be (O, {patch}) or (O, {patch}, 1, 1), got {tuple(weight.shape)}")
+        dev = U.same_device(in1, in2, wt)
+        if U._lib.load().pmt_corr1d_conv_relu_supported(C, H, W, patch, O) != 1:
+            raise NotImplementedError(
+                f"correlation_conv1x1_relu covers patch (1,17), 16 <= W <= 128, W % 4 == 0, O <= 256; got patch (1,{patch}), "
+                f"W={W}, O={O} -- use SpatialCorrelationSampler + Conv2d + ReLU for this shape (no silent fallback)")
+        z = torch.empty((B, O, H, W), device=dev, dtype=torch.float32)
+        corr = torch.empty((B, patch, H, W), device=dev, dtype=torch.float32)
+        U.call("pmt_corr1d_conv_relu_fwd_f32", dev, U.ptr(in1), U.ptr(in2), U.ptr(wt), U.ptr(z), U.ptr(corr), B, C, H, W,
+               patch, O)
+        ctx.save_for_backward(in1, in2, wt, z, corr)
+        ctx.wshape = weight.shape
+        return z
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, gz):
+        in1, in2, wt, z, corr = ctx.saved_tensors
+        B, C, H, W = in1.shape
+        O, P = wt.size(0), corr.size(1)
+        g = U.require_cuda_f32(gz, "grad_output")
+        g1, g2 = torch.empty_like(in1), torch.empty_like(in2)
+        gw = torch.empty((O, P), device=in1.device, dtype=torch.float32)
+        work = torch.empty((B * H, O * P), device=in1.device, dtype=torch.float32)
+        U.call("pmt_corr1d_conv_relu_bwd_f32", in1.device, U.ptr(in1), U.ptr(in2), U.ptr(wt), U.ptr(z), U.ptr(corr), U.ptr(g),
+               U.ptr(g1), U.ptr(g2), U.ptr(gw), U.ptr(work), B, C, H, W, P, O)
+        return g1, g2, gw.view(ctx.wshape), None
+
+
+def correlation_conv1x1_relu(input1, input2, weight, patch_size=(1, 17)):
+    """Fused form of models/dsnet_t2.py:1187-1197 (and :879-888, models/dsnet_t2_warp.py:664-671) for `-corrType 1dcorr`::
+
+        y = torch.squeeze(correlation_sampler(a, b), dim=1)        # (B, P, H, W), not divided by C
+        y = corrConv2d(y)                                          # conv2dSame(P, O, 1) without bias, then ReLU
+
+    `weight` is the 1x1 convolution's weight, (O, P, 1, 1) or (O, P).  Returns (B, O, H, W).  The (B,P,H,W) slab stays in
+    shared memory; differentiable in input1, input2 and weight (deterministic)."""
+    pH, pW = U.pair(patch_size, "patch_size")
+    if pH != 1:
+        raise NotImplementedError("correlation_conv1x1_relu implements the 1 x P horizontal patch (`-corrType 1dcorr`)")
+    return _CorrConvReLU.apply(input1, input2, weight, pW)
+
+
+class CorrelationConvReLU(nn.Module):
+    """`correlation_sampler` + `corrConv2d` of the reference's 1dcorr models as one module.  Build it from the two
+    reference sub-modules with `CorrelationConvReLU.from_reference(model.correlation_sampler, model.corrConv2d)`: the
+    convolution's weight Parameter is shared, not copied, so optimisers and checkpoints see the same tensor."""
+
+    def __init__(self, patch_size=(1, 17), out_channels=128):
+        super().__init__()
+        self.patch_size = U.pair(patch_size, "patch_size")
+        self.weight = nn.Parameter(torch.empty(out_channels, self.patch_size[1], 1, 1))
+        # conv2dSame's init (models/torch_model.py:261-264): N(0, sqrt(2 / (k*k*out_channels)))
+        nn.init.normal_(self.weight, 0.0, (2.0 / out_channels) ** 0.5)
+
+    @classmethod
+    def from_reference(cls, correlation_sampler, corr_conv2d):
+        conv = None
+        for m in corr_conv2d.modules():
+            if isinstance(m, nn.Conv2d):
+                conv = m
+                break
+        if conv is None or conv.kernel_size != (1, 1) or conv.bias is not None:
+            raise ValueError("corrConv2d must hold a bias-free 1x1 nn.Conv2d followed by ReLU (conv2dSame(P, O, 1) + ReLU)")
+        self = cls(correlation_sampler.patch_size, conv.out_channels)
+        self.weight = conv.weight
+        return self
+
+    def forward(self, input1, input2):
+        return correlation_conv1x1_relu(input1, input2, self.weight, self.patch_size)

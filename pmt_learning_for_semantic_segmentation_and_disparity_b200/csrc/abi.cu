@@ -48,10 +48,27 @@ int launch_bn_pair_bwd_reduce(const float*, const float*, const float*, const fl
                               const float*, const float*, int, cudaStream_t);
 int launch_bn_pair_bwd_apply(const float*, const float*, const float*, const float*, const float*, const float*, float*, int,
                              int, int, const float*, int, cudaStream_t);
+int launch_bn_pair_stats_peer(const float*, void* const*, void*, int, int, long long, long long, int*, unsigned*, int*, int, int, int,
+                              cudaStream_t);
+int launch_bn_pair_apply_peer(const float*, void*, int, long long, long long, int*, int*, const float*, const float*, float*,
+                              float*, float, float, float*, float*, float*, int, int, int, int, cudaStream_t);
+int launch_bn_pair_bwd_reduce_peer(const float*, const float*, const float*, const float*, void* const*, void*, int, int,
+                                   long long, long long, int*, unsigned*, int*, float*, float*, int, int, int, const float*,
+                                   const float*, int, cudaStream_t);
+int launch_bn_pair_bwd_apply_peer(const float*, const float*, const float*, const float*, const float*, void*, int, long long,
+                                  long long, int*, int*, float*, int, int, int, const float*, int, cudaStream_t);
 int launch_warp_fwd(const float*, const float*, float*, int, int, int, int, int, cudaStream_t);
 int launch_warp_bwd(const float*, const float*, const float*, float*, float*, int, int, int, int, int,
                     cudaStream_t);
 
+bool corr2d_rows_ok(const void*, const void*, const void*, int, int, int, int, int, int, int);
+int launch_corr2d_fwd_rows(const float*, const float*, float*, int, int, int, int, int, cudaStream_t);
+int launch_corr2d_bwd_rows(const float*, const float*, const float*, float*, float*, int, int, int, int, int, cudaStream_t);
+int corr_conv_relu_supported(int, int, int, int, int);
+int launch_corr_conv_relu_fwd(const float*, const float*, const float*, float*, float*, int, int, int, int, int, int,
+                              cudaStream_t);
+int launch_corr_conv_relu_bwd(const float*, const float*, const float*, const float*, const float*, const float*, float*,
+                              float*, float*, float*, int, int, int, int, int, int, cudaStream_t);
 bool warp_rows_supported(int, int, int);
 int launch_warp_blend_fwd(const float*, const float*, const float*, const float*, float*, float*, int, int, int, int,
                           cudaStream_t);
@@ -256,10 +273,14 @@ int pmt_corr1d_bwd_f32(const float* in1, const float* in2, const float* gout, fl
   PMT_CHECK_ARG(gin1 && gin2, "correlation backward: null gradient pointer");
   if ((int64_t)B * C * H * W == 0) return PMT_OK;
   if (aligned16(gout) && aligned16(gin1) && aligned16(gin2)) {
-    if (PMT_ENV_INT("PMT_BWD_V1", 0) == 0 && corr1d_bwd_tca_ok(in1, in2, C, H, W, P, dilp, 3))
-      return launch_corr1d_bwd_tca(in1, in2, gout, gin1, gin2, B, C, H, W, P, 3, static_cast<cudaStream_t>(stream));
-    if (corr1d_bwd_tc_ok(in1, in2, C, H, W, P, dilp, 3))
+    // first-generation kernel (A operand of gin2 re-laid out in shared memory) where it fits: it is the faster one at
+    // the headline shape (323 vs 474 us); the second generation (both A operands in TMEM,
+    // channel blocks) takes over for C > 128 and P > 192
+    const bool gen2_first = PMT_ENV_INT("PMT_BWD_GEN2", 0) != 0;
+    if (!gen2_first && corr1d_bwd_tc_ok(in1, in2, C, H, W, P, dilp, 3))
       return launch_corr1d_bwd_tc(in1, in2, gout, gin1, gin2, B, C, H, W, P, 3, static_cast<cudaStream_t>(stream));
+    if (corr1d_bwd_tca_ok(in1, in2, C, H, W, P, dilp, 3))
+      return launch_corr1d_bwd_tca(in1, in2, gout, gin1, gin2, B, C, H, W, P, 3, static_cast<cudaStream_t>(stream));
   }
   return pmt_corr1d_bwd_simt_f32(in1, in2, gout, gin1, gin2, B, C, H, W, P, dilp, stream);
 }
@@ -282,19 +303,21 @@ int pmt_corr1d_bwd_tc_f32(const float* in1, const float* in2, const float* gout,
   PMT_CHECK_ARG(gin1 && gin2, "correlation backward: null gradient pointer");
   PMT_CHECK_ARG(passes == 1 || passes == 3, "corr1d tc: passes must be 1 (tf32) or 3 (3xtf32)");
   if ((int64_t)B * C * H * W == 0) return PMT_OK;
-  if (PMT_ENV_INT("PMT_BWD_V1", 0) == 0 && corr1d_bwd_tca_ok(in1, in2, C, H, W, P, dilp, passes) && aligned16(gout))
-    return launch_corr1d_bwd_tca(in1, in2, gout, gin1, gin2, B, C, H, W, P, passes, static_cast<cudaStream_t>(stream));
-  if (!corr1d_bwd_tc_ok(in1, in2, C, H, W, P, dilp, passes)) {
+  if (PMT_ENV_INT("PMT_BWD_GEN2", 0) == 0 && corr1d_bwd_tc_ok(in1, in2, C, H, W, P, dilp, passes))
+    return launch_corr1d_bwd_tc(in1, in2, gout, gin1, gin2, B, C, H, W, P, passes, static_cast<cudaStream_t>(stream));
+  if (!(corr1d_bwd_tca_ok(in1, in2, C, H, W, P, dilp, passes) && aligned16(gout))) {
     set_error("corr1d tc bwd: shape/alignment not supported by the tensor-core path (W%%4, 16-byte pointers, P<=256, dilp=1)");
     return PMT_ERR_UNSUPPORTED;
   }
-  return launch_corr1d_bwd_tc(in1, in2, gout, gin1, gin2, B, C, H, W, P, passes, static_cast<cudaStream_t>(stream));
+  return launch_corr1d_bwd_tca(in1, in2, gout, gin1, gin2, B, C, H, W, P, passes, static_cast<cudaStream_t>(stream));
 }
 
 int pmt_corr_fwd_f32(const float* in1, const float* in2, float* out, int B, int C, int H, int W, int pH,
                      int pW, int dpH, int dpW, void* stream) {
   if (int e = check_corr_args(in1, in2, out, B, C, H, W, pH, pW, dpH, dpW)) return e;
   if (pH == 1) return pmt_corr1d_fwd_f32(in1, in2, out, B, C, H, W, pW, dpW, stream);
+  if (corr2d_rows_ok(in1, in2, out, C, H, W, pH, pW, dpH, dpW))   // (pH,17) patches: row-pair passes through shared memory
+    return launch_corr2d_fwd_rows(in1, in2, out, B, C, H, W, pH, static_cast<cudaStream_t>(stream));
   return launch_corr_generic_fwd(in1, in2, out, B, C, H, W, pH, pW, dpH, dpW, static_cast<cudaStream_t>(stream));
 }
 
@@ -303,6 +326,8 @@ int pmt_corr_bwd_f32(const float* in1, const float* in2, const float* gout, floa
   if (int e = check_corr_args(in1, in2, gout, B, C, H, W, pH, pW, dpH, dpW)) return e;
   PMT_CHECK_ARG(gin1 && gin2, "correlation backward: null gradient pointer");
   if (pH == 1) return pmt_corr1d_bwd_f32(in1, in2, gout, gin1, gin2, B, C, H, W, pW, dpW, stream);
+  if (corr2d_rows_ok(in1, in2, gout, C, H, W, pH, pW, dpH, dpW) && aligned16(gin1) && aligned16(gin2))
+    return launch_corr2d_bwd_rows(in1, in2, gout, gin1, gin2, B, C, H, W, pH, static_cast<cudaStream_t>(stream));
   return launch_corr_generic_bwd(in1, in2, gout, gin1, gin2, B, C, H, W, pH, pW, dpH, dpW,
                                  static_cast<cudaStream_t>(stream));
 }
@@ -388,6 +413,59 @@ int pmt_bn_pair_bwd_apply_f32(const float* dy, const float* x, const float* save
                                   static_cast<cudaStream_t>(stream));
 }
 
+static int check_peer(const void* bufs_or_local, int world, int rank, int64_t payload_off, int64_t flag_off, const void* epoch,
+                      const void* err) {
+  PMT_CHECK_ARG(bufs_or_local && epoch && err, "bn_pair peer exchange: null pointer");
+  PMT_CHECK_ARG(world >= 1 && rank >= 0 && rank < world && payload_off >= 0 && flag_off >= 0, "bn_pair peer exchange: bad rank/offset");
+  return PMT_OK;
+}
+
+int pmt_bn_pair_stats_peer_f32(const float* x, void* const* peer_bufs, void* local_buf, int world, int rank,
+                               int64_t payload_off, int64_t flag_off, int* epoch, unsigned* done, int* err, int B, int C,
+                               int HW, void* stream) {
+  PMT_CHECK_ARG(x && local_buf && done, "bn_pair: null pointer");
+  PMT_CHECK_ARG(B >= 0 && C >= 0 && HW >= 0, "bn_pair: negative dimension");
+  if (int e = check_peer(peer_bufs, world, rank, payload_off, flag_off, epoch, err)) return e;
+  return launch_bn_pair_stats_peer(x, peer_bufs, local_buf, world, rank, payload_off, flag_off, epoch, done, err, B, C, HW,
+                                   static_cast<cudaStream_t>(stream));
+}
+
+int pmt_bn_pair_apply_peer_f32(const float* x, void* local_buf, int world, int64_t payload_off, int64_t flag_off, int* epoch,
+                               int* err, const float* weight, const float* bias, float* running_mean, float* running_var,
+                               float momentum, float eps, float* out, float* save_mean, float* save_invstd, int B, int C,
+                               int HW, int relu, void* stream) {
+  PMT_CHECK_ARG(x && out && save_mean && save_invstd, "bn_pair: null pointer");
+  PMT_CHECK_ARG(B >= 0 && C >= 0 && HW >= 0, "bn_pair: bad dimension");
+  PMT_CHECK_ARG((running_mean == nullptr) == (running_var == nullptr), "bn_pair: running_mean/var must both be given or both NULL");
+  if (int e = check_peer(local_buf, world, 0, payload_off, flag_off, epoch, err)) return e;
+  return launch_bn_pair_apply_peer(x, local_buf, world, payload_off, flag_off, epoch, err, weight, bias, running_mean,
+                                   running_var, momentum, eps, out, save_mean, save_invstd, B, C, HW, relu,
+                                   static_cast<cudaStream_t>(stream));
+}
+
+int pmt_bn_pair_bwd_reduce_peer_f32(const float* dy, const float* x, const float* save_mean, const float* save_invstd,
+                                    void* const* peer_bufs, void* local_buf, int world, int rank, int64_t payload_off,
+                                    int64_t flag_off, int* epoch, unsigned* done, int* err, float* gw, float* gb, int B, int C,
+                                    int HW, const float* weight, const float* bias, int relu, void* stream) {
+  PMT_CHECK_ARG(dy && x && save_mean && save_invstd && gw && gb && local_buf && done, "bn_pair: null pointer");
+  PMT_CHECK_ARG(B >= 0 && C >= 0 && HW >= 0, "bn_pair: negative dimension");
+  if (int e = check_peer(peer_bufs, world, rank, payload_off, flag_off, epoch, err)) return e;
+  return launch_bn_pair_bwd_reduce_peer(dy, x, save_mean, save_invstd, peer_bufs, local_buf, world, rank, payload_off, flag_off,
+                                        epoch, done, err, gw, gb, B, C, HW, weight, bias, relu,
+                                        static_cast<cudaStream_t>(stream));
+}
+
+int pmt_bn_pair_bwd_apply_peer_f32(const float* dy, const float* x, const float* save_mean, const float* save_invstd,
+                                   const float* weight, void* local_buf, int world, int64_t payload_off, int64_t flag_off,
+                                   int* epoch, int* err, float* dx, int B, int C, int HW, const float* bias, int relu,
+                                   void* stream) {
+  PMT_CHECK_ARG(dy && x && save_mean && save_invstd && dx, "bn_pair: null pointer");
+  PMT_CHECK_ARG(B >= 0 && C >= 0 && HW >= 0, "bn_pair: negative dimension");
+  if (int e = check_peer(local_buf, world, 0, payload_off, flag_off, epoch, err)) return e;
+  return launch_bn_pair_bwd_apply_peer(dy, x, save_mean, save_invstd, weight, local_buf, world, payload_off, flag_off, epoch,
+                                       err, dx, B, C, HW, bias, relu, static_cast<cudaStream_t>(stream));
+}
+
 int pmt_upsample_softargmin_bwd_supported(int B, int Dq, int Hq, int Wq, int D, int H, int W) {
   return upsample_softargmin_bwd_supported(B, Dq, Hq, Wq, D, H, W);
 }
@@ -414,6 +492,35 @@ int pmt_warp1d_bwd_f32(const float* img, const float* off, const float* gout, fl
   PMT_CHECK_ARG(gimg || goff, "warp backward: nothing to compute");
   PMT_CHECK_ARG(N >= 0 && C >= 0 && H >= 0 && W >= 0, "warp: negative dimension");
   return launch_warp_bwd(img, off, gout, gimg, goff, N, C, H, W, gout_cnhw, static_cast<cudaStream_t>(stream));
+}
+
+int pmt_corr1d_conv_relu_supported(int C, int H, int W, int P, int O) { return corr_conv_relu_supported(C, H, W, P, O); }
+
+int pmt_corr1d_conv_relu_fwd_f32(const float* in1, const float* in2, const float* weight, float* z, float* corr_save, int B,
+                                 int C, int H, int W, int P, int O, void* stream) {
+  PMT_CHECK_ARG(in1 && in2 && weight && z && corr_save, "corr+conv+relu: null pointer");
+  PMT_CHECK_ARG(B >= 0 && C >= 1 && H >= 0 && W >= 1 && P >= 1 && O >= 1, "corr+conv+relu: bad dimension");
+  PMT_CHECK_ARG(aligned16(in1) && aligned16(in2), "corr+conv+relu: inputs must be 16-byte aligned");
+  if (!corr_conv_relu_supported(C, H, W, P, O)) {
+    set_error("corr+conv+relu: shape not covered by the fused kernels (P=17, 16<=W<=128, W%%4==0, O<=256)");
+    return PMT_ERR_UNSUPPORTED;
+  }
+  return launch_corr_conv_relu_fwd(in1, in2, weight, z, corr_save, B, C, H, W, P, O, static_cast<cudaStream_t>(stream));
+}
+
+int pmt_corr1d_conv_relu_bwd_f32(const float* in1, const float* in2, const float* weight, const float* z,
+                                 const float* corr_save, const float* gz, float* gin1, float* gin2, float* gweight,
+                                 float* workspace, int B, int C, int H, int W, int P, int O, void* stream) {
+  PMT_CHECK_ARG(in1 && in2 && weight && z && corr_save && gz && gin1 && gin2 && gweight && workspace,
+                "corr+conv+relu backward: null pointer");
+  PMT_CHECK_ARG(B >= 0 && C >= 1 && H >= 0 && W >= 1 && P >= 1 && O >= 1, "corr+conv+relu: bad dimension");
+  PMT_CHECK_ARG(aligned16(in1) && aligned16(in2) && aligned16(gin1) && aligned16(gin2), "corr+conv+relu: 16-byte alignment");
+  if (!corr_conv_relu_supported(C, H, W, P, O)) {
+    set_error("corr+conv+relu: shape not covered by the fused kernels (P=17, 16<=W<=128, W%%4==0, O<=256)");
+    return PMT_ERR_UNSUPPORTED;
+  }
+  return launch_corr_conv_relu_bwd(in1, in2, weight, z, corr_save, gz, gin1, gin2, gweight, workspace, B, C, H, W, P, O,
+                                   static_cast<cudaStream_t>(stream));
 }
 
 int pmt_warp1d_rows_supported(int N, int H, int W) { return warp_rows_supported(N, H, W) ? 1 : 0; }

@@ -10,7 +10,21 @@
 //                        applies the affine map, saves mean / invstd, updates the running statistics (left, then right)
 //   bn_pair_bwd_reduce : per (half, channel) sum_dy and sum_dy*(x-mean); grad_weight / grad_bias (local)
 //   bn_pair_bwd_apply  : dx = (dy - sum_dy/N - (x-mean) * invstd^2 * sum_dy_xmu/N) * invstd * w
-// All tensors are NCHW fp32, contiguous.  The collectives themselves stay in torch.distributed (NCCL).
+// All tensors are NCHW fp32, contiguous.
+//
+// Cross-rank exchange.  Either the caller runs the collective between the two kernels of a direction (torch.distributed:
+// all_gather of the stats payload, all_reduce of the backward sums) -- or, with a PeerX descriptor, the kernels exchange
+// the payload themselves over NVLink peer memory, with NO collective launch on the dependency chain (a BN cannot
+// normalise before the statistics of all ranks are there, so the ~40 us an NCCL launch costs inside a CUDA graph is
+// paid once per layer and direction; it is what limited the 8-GPU training step to 5.7x):
+//   producer (stats / bwd_reduce): every block stores its (half, channel) pair straight into the symmetric buffer of
+//     EVERY rank (slot [parity][my rank]), __threadfence_system(), and counts itself on a local counter; the last block
+//     bumps the local epoch and writes it, st.release.sys, into the flag [parity][my rank] of every rank;
+//   consumer (apply / bwd_apply): every block spins (ld.acquire.sys) until the `world` flags of the current parity show
+//     the local epoch, then reads the payloads from its OWN copy of the buffer (peers pushed them) with ld.cg.
+//   Slots are double-buffered by epoch parity, the epoch lives in device memory and advances inside the producer kernel,
+//   so a captured CUDA graph replays correctly.  A rank that waits longer than ~2 s sets *err and stops waiting (a hung
+//   peer must not hang this GPU).
 #include "common.cuh"
 
 namespace pmt {
@@ -22,6 +36,57 @@ __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
   return v;
+}
+
+// ---- NVLink peer exchange (see the header comment) ----
+struct PeerX {
+  float* const* bufs;     // device array [world]: base pointer of every rank's symmetric buffer (own rank included)
+  float* local;           // this rank's buffer (= bufs[rank], passed separately so consumers need no indirection)
+  int world, rank;
+  long long payload_off;  // float offset of this layer+direction's payload region [2 parity][world][n]
+  long long flag_off;     // float offset of its flags [2 parity][world] (int32)
+  int n;                  // payload floats per rank
+  int* epoch;             // local device counter of this layer+direction (starts at 0)
+  unsigned* done;         // local block counter (starts at 0; the last block resets it)
+  int* err;               // set to 1 when a wait timed out
+};
+
+__device__ __forceinline__ void st_release_sys(int* p, int v) {
+  asm volatile("st.release.sys.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ int ld_acquire_sys(const int* p) {
+  int v;
+  asm volatile("ld.acquire.sys.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+
+// producer side, called by ONE thread per block after it has stored its payload values to every peer
+__device__ __forceinline__ void peer_publish(const PeerX& px, int e_next, unsigned n_blocks) {
+  __threadfence_system();                                   // this block's peer stores are visible system-wide
+  if (atomicAdd(px.done, 1u) == n_blocks - 1) {             // last block of the grid
+    *px.done = 0u;
+    *px.epoch = e_next;                                     // read by the consumer kernel that follows in the stream
+    __threadfence_system();
+    const int par = e_next & 1;
+    for (int r = 0; r < px.world; ++r)
+      st_release_sys(reinterpret_cast<int*>(px.bufs[r] + px.flag_off) + par * px.world + px.rank, e_next);
+  }
+}
+
+// consumer side: returns the base of the [world][n] payloads of the current epoch once every rank has published
+__device__ __forceinline__ const float* peer_wait(const PeerX& px) {
+  const int e = *px.epoch, par = e & 1;
+  const int* flags = reinterpret_cast<const int*>(px.local + px.flag_off) + par * px.world;
+  const long long t0 = clock64();
+  for (int r = 0; r < px.world; ++r) {
+    while (ld_acquire_sys(flags + r) != e) {
+      if (clock64() - t0 > (1ll << 32)) {                   // ~2 s: give up instead of hanging the GPU
+        *px.err = 1;
+        break;
+      }
+    }
+  }
+  return px.local + px.payload_off + (long long)par * px.world * px.n;
 }
 
 // block-wide sum of two values; result valid in every thread
@@ -59,7 +124,7 @@ __device__ __forceinline__ void for_channel(const float* __restrict__ x, int hal
 // grid (C, 2).  Single pass with shifted sums (shift = first element of the channel): mean = K + S1/n,
 // M2 = S2 - S1^2/n -- as accurate as a two-pass algorithm unless the channel is constant to 7 digits.
 __global__ void __launch_bounds__(kBnThreads) bn_pair_stats_kernel(const float* __restrict__ x, float* __restrict__ payload,
-                                                                   int B, int C, int HW) {
+                                                                   int B, int C, int HW, const PeerX px) {
   const int c = blockIdx.x, half = blockIdx.y;
   const float K = __ldg(x + ((int64_t)(half * B) * C + c) * HW);
   float s1 = 0.f, s2 = 0.f;
@@ -71,27 +136,41 @@ __global__ void __launch_bounds__(kBnThreads) bn_pair_stats_kernel(const float* 
   block_sum2(s1, s2);
   if (threadIdx.x == 0) {
     const float n = (float)B * (float)HW;
-    payload[(half * C + c) * 2 + 0] = K + s1 / n;
-    payload[(half * C + c) * 2 + 1] = fmaxf(s2 - s1 * s1 / n, 0.f);
-    if (c == 0 && half == 0) payload[4 * C] = n;   // this rank's element count per channel-half
+    const float mean = K + s1 / n, m2 = fmaxf(s2 - s1 * s1 / n, 0.f);
+    if (px.bufs == nullptr) {
+      payload[(half * C + c) * 2 + 0] = mean;
+      payload[(half * C + c) * 2 + 1] = m2;
+      if (c == 0 && half == 0) payload[4 * C] = n;   // this rank's element count per channel-half
+    } else {
+      const int e_next = *px.epoch + 1;              // every block reads the same value: only the last block advances it
+      const long long slot = px.payload_off + ((long long)(e_next & 1) * px.world + px.rank) * px.n;
+      for (int r = 0; r < px.world; ++r) {
+        float* dst = px.bufs[r] + slot;
+        dst[(half * C + c) * 2 + 0] = mean;
+        dst[(half * C + c) * 2 + 1] = m2;
+        if (c == 0 && half == 0) dst[4 * C] = n;
+      }
+      peer_publish(px, e_next, gridDim.x * gridDim.y);
+    }
   }
 }
 
 // Chan et al.: combine (n_r, mean_r, M2_r) of `world` ranks.  gathered = [world][4C+1]: [half][c][2] then the count.
 __device__ __forceinline__ void combine(const float* __restrict__ gathered, int world, int stride, int half, int c, int C,
                                         float& mean, float& var_biased, float& n_total) {
+  // ld.cg: with the peer exchange the payloads were written by other GPUs (never read them through L1)
   float N = 0.f, m = 0.f;
   for (int r = 0; r < world; ++r) {
-    const float n = gathered[r * stride + 4 * C];
+    const float n = __ldcg(gathered + r * stride + 4 * C);
     N += n;
-    m = fmaf(n, gathered[r * stride + (half * C + c) * 2], m);
+    m = fmaf(n, __ldcg(gathered + r * stride + (half * C + c) * 2), m);
   }
   m /= N;
   float M2 = 0.f;
   for (int r = 0; r < world; ++r) {
-    const float n = gathered[r * stride + 4 * C];
-    const float d = gathered[r * stride + (half * C + c) * 2] - m;
-    M2 += gathered[r * stride + (half * C + c) * 2 + 1] + n * d * d;
+    const float n = __ldcg(gathered + r * stride + 4 * C);
+    const float d = __ldcg(gathered + r * stride + (half * C + c) * 2) - m;
+    M2 += __ldcg(gathered + r * stride + (half * C + c) * 2 + 1) + n * d * d;
   }
   mean = m, var_biased = M2 / N, n_total = N;
 }
@@ -103,11 +182,12 @@ __global__ void __launch_bounds__(kBnThreads) bn_pair_apply_kernel(const float* 
                                                                    float* running_var, float momentum, float eps,
                                                                    float* __restrict__ out, float* __restrict__ save_mean,
                                                                    float* __restrict__ save_invstd, int B, int C, int HW,
-                                                                   int relu) {
+                                                                   int relu, const PeerX px) {
   const int row = blockIdx.x, b = row / C, c = row % C, half = b >= B ? 1 : 0;
   const int stride = 4 * C + 1;
   __shared__ float s_scale, s_shift;
   if (threadIdx.x == 0) {
+    if (px.bufs != nullptr) gathered = peer_wait(px);   // every rank's payload has landed in this rank's buffer
     float mean, var, N;
     combine(gathered, world, stride, half, c, C, mean, var, N);
     const float invstd = rsqrtf(var + eps);
@@ -155,7 +235,8 @@ __global__ void __launch_bounds__(kBnThreads) bn_pair_bwd_reduce_kernel(const fl
                                                                         float* __restrict__ sums, float* __restrict__ gw,
                                                                         float* __restrict__ gb, int B, int C, int HW,
                                                                         const float* __restrict__ weight,
-                                                                        const float* __restrict__ bias, int relu) {
+                                                                        const float* __restrict__ bias, int relu,
+                                                                        const PeerX px) {
   const int c = blockIdx.x, half = blockIdx.y;
   const float mean = save_mean[half * C + c];
   // fused ReLU: the incoming gradient only counts where y = (x-mean)*invstd*w + b was positive (y recomputed from x)
@@ -186,11 +267,22 @@ __global__ void __launch_bounds__(kBnThreads) bn_pair_bwd_reduce_kernel(const fl
   }
   block_sum2(s1, s2);
   if (threadIdx.x == 0) {
-    sums[(half * C + c) * 2 + 0] = s1;
-    sums[(half * C + c) * 2 + 1] = s2;
     // gw/gb are zero-filled by the caller
     atomicAdd(gw + c, s2 * save_invstd[half * C + c]);
     atomicAdd(gb + c, s1);
+    if (px.bufs == nullptr) {
+      sums[(half * C + c) * 2 + 0] = s1;
+      sums[(half * C + c) * 2 + 1] = s2;
+    } else {
+      const int e_next = *px.epoch + 1;
+      const long long slot = px.payload_off + ((long long)(e_next & 1) * px.world + px.rank) * px.n;
+      for (int r = 0; r < px.world; ++r) {
+        float* dst = px.bufs[r] + slot;
+        dst[(half * C + c) * 2 + 0] = s1;
+        dst[(half * C + c) * 2 + 1] = s2;
+      }
+      peer_publish(px, e_next, gridDim.x * gridDim.y);
+    }
   }
 }
 
@@ -201,15 +293,30 @@ __global__ void __launch_bounds__(kBnThreads) bn_pair_bwd_apply_kernel(const flo
                                                                        const float* __restrict__ weight,
                                                                        const float* __restrict__ sums,
                                                                        float* __restrict__ dx, int B, int C, int HW,
-                                                                       const float* __restrict__ bias, int relu) {
+                                                                       const float* __restrict__ bias, int relu,
+                                                                       const PeerX px) {
   const int row = blockIdx.x, b = row / C, c = row % C, half = b >= B ? 1 : 0;
   const float mean = save_mean[half * C + c], invstd = save_invstd[half * C + c];
+  __shared__ float s_sum[2];
+  if (px.bufs != nullptr) {
+    // all-reduce in place of NCCL: wait for every rank's sums, add them in rank order (identical on all ranks)
+    if (threadIdx.x == 0) {
+      const float* all = peer_wait(px);
+      float a0 = 0.f, a1 = 0.f;
+      for (int r = 0; r < px.world; ++r) {
+        a0 += __ldcg(all + (long long)r * px.n + (half * C + c) * 2);
+        a1 += __ldcg(all + (long long)r * px.n + (half * C + c) * 2 + 1);
+      }
+      s_sum[0] = a0, s_sum[1] = a1;
+    }
+    __syncthreads();
+  }
   const float w = weight ? weight[c] : 1.f;
   const float ysc = invstd * w, ysh = (bias ? bias[c] : 0.f) - mean * ysc;
   auto gate = [&](float g, float v) { return (!relu || fmaf(v, ysc, ysh) > 0.f) ? g : 0.f; };
   const float n_total = save_invstd[2 * C];
-  const float mean_dy = sums[(half * C + c) * 2] / n_total;
-  const float k = sums[(half * C + c) * 2 + 1] / n_total * invstd * invstd;
+  const float mean_dy = (px.bufs != nullptr ? s_sum[0] : sums[(half * C + c) * 2]) / n_total;
+  const float k = (px.bufs != nullptr ? s_sum[1] : sums[(half * C + c) * 2 + 1]) / n_total * invstd * invstd;
   const float sc = invstd * w;
   const float* g = dy + (int64_t)row * HW;
   const float* xr = x + (int64_t)row * HW;
@@ -233,9 +340,20 @@ __global__ void __launch_bounds__(kBnThreads) bn_pair_bwd_apply_kernel(const flo
 
 }  // namespace
 
+namespace {
+PeerX make_px(void* const* bufs, void* local, int world, int rank, long long payload_off, long long flag_off, int n, int* epoch,
+              unsigned* done, int* err) {
+  PeerX px{};
+  px.bufs = reinterpret_cast<float* const*>(bufs), px.local = static_cast<float*>(local);
+  px.world = world, px.rank = rank, px.payload_off = payload_off, px.flag_off = flag_off, px.n = n;
+  px.epoch = epoch, px.done = done, px.err = err;
+  return px;
+}
+}  // namespace
+
 int launch_bn_pair_stats(const float* x, float* payload, int B, int C, int HW, cudaStream_t st) {
   if (B == 0 || C == 0 || HW == 0) return PMT_OK;
-  bn_pair_stats_kernel<<<dim3((unsigned)C, 2), kBnThreads, 0, st>>>(x, payload, B, C, HW);
+  bn_pair_stats_kernel<<<dim3((unsigned)C, 2), kBnThreads, 0, st>>>(x, payload, B, C, HW, PeerX{});
   PMT_LAUNCH_OK("bn_pair_stats_kernel");
   return PMT_OK;
 }
@@ -245,7 +363,8 @@ int launch_bn_pair_apply(const float* x, const float* gathered, int world, const
                          float* save_invstd, int B, int C, int HW, int relu, cudaStream_t st) {
   if (B == 0 || C == 0 || HW == 0) return PMT_OK;
   bn_pair_apply_kernel<<<(unsigned)(2 * B * C), kBnThreads, 0, st>>>(x, gathered, world, weight, bias, running_mean, running_var,
-                                                                    momentum, eps, out, save_mean, save_invstd, B, C, HW, relu);
+                                                                    momentum, eps, out, save_mean, save_invstd, B, C, HW, relu,
+                                                                    PeerX{});
   PMT_LAUNCH_OK("bn_pair_apply_kernel");
   return PMT_OK;
 }
@@ -255,7 +374,7 @@ int launch_bn_pair_bwd_reduce(const float* dy, const float* x, const float* save
                               cudaStream_t st) {
   if (B == 0 || C == 0 || HW == 0) return PMT_OK;
   bn_pair_bwd_reduce_kernel<<<dim3((unsigned)C, 2), kBnThreads, 0, st>>>(dy, x, save_mean, save_invstd, sums, gw, gb, B, C, HW,
-                                                                         weight, bias, relu);
+                                                                         weight, bias, relu, PeerX{});
   PMT_LAUNCH_OK("bn_pair_bwd_reduce_kernel");
   return PMT_OK;
 }
@@ -265,8 +384,55 @@ int launch_bn_pair_bwd_apply(const float* dy, const float* x, const float* save_
                              cudaStream_t st) {
   if (B == 0 || C == 0 || HW == 0) return PMT_OK;
   bn_pair_bwd_apply_kernel<<<(unsigned)(2 * B * C), kBnThreads, 0, st>>>(dy, x, save_mean, save_invstd, weight, sums, dx, B, C,
-                                                                        HW, bias, relu);
+                                                                        HW, bias, relu, PeerX{});
   PMT_LAUNCH_OK("bn_pair_bwd_apply_kernel");
+  return PMT_OK;
+}
+
+// ---- the same four steps with the NVLink peer exchange instead of a collective between them ----
+int launch_bn_pair_stats_peer(const float* x, void* const* bufs, void* local, int world, int rank, long long payload_off,
+                              long long flag_off, int* epoch, unsigned* done, int* err, int B, int C, int HW, cudaStream_t st) {
+  if (B == 0 || C == 0 || HW == 0) return PMT_OK;
+  bn_pair_stats_kernel<<<dim3((unsigned)C, 2), kBnThreads, 0, st>>>(
+      x, nullptr, B, C, HW, make_px(bufs, local, world, rank, payload_off, flag_off, 4 * C + 1, epoch, done, err));
+  PMT_LAUNCH_OK("bn_pair_stats_kernel<peer>");
+  return PMT_OK;
+}
+
+int launch_bn_pair_apply_peer(const float* x, void* local, int world, long long payload_off, long long flag_off, int* epoch,
+                              int* err, const float* weight, const float* bias, float* running_mean, float* running_var,
+                              float momentum, float eps, float* out, float* save_mean, float* save_invstd, int B, int C, int HW,
+                              int relu, cudaStream_t st) {
+  if (B == 0 || C == 0 || HW == 0) return PMT_OK;
+  // bufs is only dereferenced by producers; a non-null marker switches the consumer to the peer path
+  bn_pair_apply_kernel<<<(unsigned)(2 * B * C), kBnThreads, 0, st>>>(
+      x, nullptr, world, weight, bias, running_mean, running_var, momentum, eps, out, save_mean, save_invstd, B, C, HW, relu,
+      make_px(reinterpret_cast<void* const*>(local), local, world, 0, payload_off, flag_off, 4 * C + 1, epoch, nullptr, err));
+  PMT_LAUNCH_OK("bn_pair_apply_kernel<peer>");
+  return PMT_OK;
+}
+
+int launch_bn_pair_bwd_reduce_peer(const float* dy, const float* x, const float* save_mean, const float* save_invstd,
+                                   void* const* bufs, void* local, int world, int rank, long long payload_off,
+                                   long long flag_off, int* epoch, unsigned* done, int* err, float* gw, float* gb, int B, int C,
+                                   int HW, const float* weight, const float* bias, int relu, cudaStream_t st) {
+  if (B == 0 || C == 0 || HW == 0) return PMT_OK;
+  bn_pair_bwd_reduce_kernel<<<dim3((unsigned)C, 2), kBnThreads, 0, st>>>(
+      dy, x, save_mean, save_invstd, nullptr, gw, gb, B, C, HW, weight, bias, relu,
+      make_px(bufs, local, world, rank, payload_off, flag_off, 4 * C, epoch, done, err));
+  PMT_LAUNCH_OK("bn_pair_bwd_reduce_kernel<peer>");
+  return PMT_OK;
+}
+
+int launch_bn_pair_bwd_apply_peer(const float* dy, const float* x, const float* save_mean, const float* save_invstd,
+                                  const float* weight, void* local, int world, long long payload_off, long long flag_off,
+                                  int* epoch, int* err, float* dx, int B, int C, int HW, const float* bias, int relu,
+                                  cudaStream_t st) {
+  if (B == 0 || C == 0 || HW == 0) return PMT_OK;
+  bn_pair_bwd_apply_kernel<<<(unsigned)(2 * B * C), kBnThreads, 0, st>>>(
+      dy, x, save_mean, save_invstd, weight, nullptr, dx, B, C, HW, bias, relu,
+      make_px(reinterpret_cast<void* const*>(local), local, world, 0, payload_off, flag_off, 4 * C, epoch, nullptr, err));
+  PMT_LAUNCH_OK("bn_pair_bwd_apply_kernel<peer>");
   return PMT_OK;
 }
 

@@ -141,6 +141,10 @@ __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc, boo
                "l"(gsrc), "r"(sz)
                : "memory");
 }
+// 4-byte variant for rows whose start is not 16-byte aligned
+__device__ __forceinline__ void cp_async4(void* smem_dst, const void* gsrc) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(smem_dst)), "l"(gsrc) : "memory");
+}
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N>
 __device__ __forceinline__ void cp_async_wait() {

@@ -197,6 +197,15 @@ corr1d_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmIn1, const __grid_con
     tc::tmem_alloc(tmem_slot, (uint32_t)a.tmem_cols);
     tc::tmem_relinquish();
   }
+  if (mode == 0) {
+    // The resident g slice sits one row down: row 0 and the rows after plane P-1 are zero and never written by the TMA,
+    // so a builder clamps the plane of an element into [-1, P] with one unsigned min and loads unconditionally
+    // (the predicated loads compiled into a divergent branch per element).
+    float* Z = reinterpret_cast<float*>(smem);
+    for (int i = tid; i < kTM; i += blockDim.x) Z[i] = 0.f;
+    for (int i = (a.P + 1) * kTM + tid; i < (a.n_gboxes * 32 + 2) * kTM; i += blockDim.x) Z[i] = 0.f;
+    fence_proxy_async();
+  }
   tc::fence_before_sync();
   __syncthreads();
   tc::fence_after_sync();
@@ -245,7 +254,7 @@ corr1d_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmIn1, const __grid_con
                 mbar_arrive(&raw_full[k]);
               } else {
                 mbar_arrive_expect_tx(&raw_full[k], (uint32_t)kBox0Bytes);
-                tma_load_4d(smem + k * kBox0Bytes, &tmG0, tc_.x0, tc_.h, 32 * k, tc_.n, &raw_full[k]);
+                tma_load_4d(smem + kTM * 4 + k * kBox0Bytes, &tmG0, tc_.x0, tc_.h, 32 * k, tc_.n, &raw_full[k]);
               }
             }
           } else {
@@ -265,10 +274,10 @@ corr1d_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmIn1, const __grid_con
     }
   } else if (wid == 1) {
     // ===== MMA issuer =====
-    // One thread issues everything, so its instruction count per chunk is on the critical path (measured: with
-    // div/mod slot arithmetic and full descriptor rebuilds it was busy 92% of the time while the tensor pipe idled).
-    // Slots and phases are kept as running counters and descriptors are advanced by adding to their low word.
-    if (lane == 0) {
+    // The warp runs the loop converged (all lanes poll the barriers) and one elected lane issues, so that descriptors,
+    // slots and phases live in uniform registers and the UTCHMMA sequence is straight-line code (tc::elect_one); with
+    // the loop under `if (lane == 0)` this single thread, not the tensor pipe, was the busiest unit of the kernel.
+    {
       const uint32_t idesc = tc::make_idesc(2, 0, 0, kTM, a.Cbox);
       const uint32_t idesc2 = tc::make_idesc(2, 0, 0, kTM, 2 * a.Cbox);  // B = [band_hi ; band_lo] stacked along N
       const uint64_t dA0 = tc::smem_desc(smem_u32(gd_ring), 16, 1024, 2);
@@ -284,52 +293,48 @@ corr1d_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmIn1, const __grid_con
         tc::fence_after_sync();
         const uint32_t d_tmem = tmem_base + (uint32_t)(buf * a.acc_cols);
         for (int k = 0; k < a.NKC; ++k) {
-          PTRACE(1, i * a.NKC + k, 0);
           PWAIT(1, &gd_built[gs], gph);
           if (kPasses == 1) PWAIT(2, &band_full[bs], bph);
-          PTRACE(1, i * a.NKC + k, 1);
           tc::fence_after_sync();
           const uint64_t dB = dB0 + (uint64_t)(b_step * (uint32_t)bs);
-          { PSEC_BEGIN();
-          if (!skip) {
-            if (tmem_a) {
-              const uint32_t ta = tmem_base + (uint32_t)(a.a_base + gs * a.aslot_cols);
+          const uint32_t ta = tmem_base + (uint32_t)(a.a_base + gs * a.aslot_cols);
+          const uint64_t dA = dA0 + (uint64_t)(a_step * (uint32_t)gs);
+          if (tc::elect_one()) {
+            if (!skip) {
+              if (tmem_a) {
 #pragma unroll
-              for (int kk = 0; kk < kKC / 8; ++kk) {
-                const uint32_t acc = (k > 0 || kk > 0) ? 1u : 0u;
-                if (kPasses == 3) {
-                  tc::mma_tf32_ts(d_tmem, ta + 8 * kk, dB + 2 * kk, idesc2, acc);
-                  tc::mma_tf32_ts(d_tmem, ta + 32 + 8 * kk, dB + 2 * kk, idesc, 1u);
-                } else {
-                  tc::mma_tf32_ts(d_tmem, ta + 8 * kk, dB + 2 * kk, idesc, acc);
+                for (int kk = 0; kk < kKC / 8; ++kk) {
+                  const uint32_t acc = (k > 0 || kk > 0) ? 1u : 0u;
+                  if (kPasses == 3) {
+                    tc::mma_tf32_ts(d_tmem, ta + 8 * kk, dB + 2 * kk, idesc2, acc);
+                    tc::mma_tf32_ts(d_tmem, ta + 32 + 8 * kk, dB + 2 * kk, idesc, 1u);
+                  } else {
+                    tc::mma_tf32_ts(d_tmem, ta + 8 * kk, dB + 2 * kk, idesc, acc);
+                  }
                 }
-              }
-            } else {
-              const uint64_t dA = dA0 + (uint64_t)(a_step * (uint32_t)gs);
+              } else {
 #pragma unroll
-              for (int kk = 0; kk < kKC / 8; ++kk) {
-                const uint32_t acc = (k > 0 || kk > 0) ? 1u : 0u;
-                if (kPasses == 3) {
-                  // D[:, 0:C] += A_hi*B_hi + A_lo*B_hi ; D[:, C:2C] += A_hi*B_lo  (A_hi is read once for both B
-                  // halves; the epilogue adds the two column blocks)
-                  tc::mma_tf32(d_tmem, dA + 2 * kk, dB + 2 * kk, idesc2, acc);
-                  tc::mma_tf32(d_tmem, dA + a_lo + 2 * kk, dB + 2 * kk, idesc, 1u);
-                } else {
-                  tc::mma_tf32(d_tmem, dA + 2 * kk, dB + 2 * kk, idesc, acc);
+                for (int kk = 0; kk < kKC / 8; ++kk) {
+                  const uint32_t acc = (k > 0 || kk > 0) ? 1u : 0u;
+                  if (kPasses == 3) {
+                    // D[:, 0:C] += A_hi*B_hi + A_lo*B_hi ; D[:, C:2C] += A_hi*B_lo  (A_hi is read once for both B
+                    // halves; the epilogue adds the two column blocks)
+                    tc::mma_tf32(d_tmem, dA + 2 * kk, dB + 2 * kk, idesc2, acc);
+                    tc::mma_tf32(d_tmem, dA + a_lo + 2 * kk, dB + 2 * kk, idesc, 1u);
+                  } else {
+                    tc::mma_tf32(d_tmem, dA + 2 * kk, dB + 2 * kk, idesc, acc);
+                  }
                 }
               }
             }
+            tc::mma_commit(&gd_empty[gs]);
+            tc::mma_commit(&band_empty[bs]);
+            if (k == a.NKC - 1) tc::mma_commit(&tmem_full[buf]);
           }
-          PSEC_END(0); }
-          { PSEC_BEGIN();
-          tc::mma_commit(&gd_empty[gs]);
-          tc::mma_commit(&band_empty[bs]);
-          PSEC_END(1); }
-          PTRACE(1, i * a.NKC + k, 2);
+          __syncwarp();
           if (++gs == m.a_slots) gs = 0, gph ^= 1u;
           if (++bs == m.band_slots) bs = 0, bph ^= 1u;
         }
-        tc::mma_commit(&tmem_full[buf]);
       }
     }
   } else if (wid < 2 + kEpiWarps) {
@@ -416,10 +421,10 @@ corr1d_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmIn1, const __grid_con
             for (int c0 = 0; c0 < kCols; c0 += 16) {
               float w[16];
               const float* col = Gt + xl;
-              const unsigned pu = (unsigned)(pb + c0), Pu = (unsigned)a.P;
+              const unsigned pu1 = (unsigned)(pb + c0 + 1), Pp1 = (unsigned)a.P + 1u;
 #pragma unroll
-              for (int t = 0; t < 16; ++t)   // one unsigned compare covers p < 0 and p >= P
-                w[t] = (pu + (unsigned)t < Pu) ? col[(int)(pu + (unsigned)t) * kTM] : 0.f;
+              for (int t = 0; t < 16; ++t)   // slice row = min(plane + 1, P + 1): planes outside [0, P) hit a zero row
+                w[t] = col[min(pu1 + (unsigned)t, Pp1) * kTM];
               if PMT_DBG(a, 4) {
 #pragma unroll
                 for (int t = 0; t < 16; ++t) w[t] = 0.f;
@@ -442,10 +447,7 @@ corr1d_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmIn1, const __grid_con
               const int pb = kKC * k + 4 * c4 - m.delta - xl;  // p of column jj = 4*c4 + t is pb + t
               float v[4];
 #pragma unroll
-              for (int t = 0; t < 4; ++t) {
-                const int p = pb + t;
-                v[t] = (p >= 0 && p < a.P) ? Gt[p * kTM + xl] : 0.f;
-              }
+              for (int t = 0; t < 4; ++t) v[t] = Gt[min((unsigned)(pb + t + 1), (unsigned)a.P + 1u) * kTM + xl];
               const uint32_t off = kmajor_off(xl, 4 * c4);
               *reinterpret_cast<float4*>(sa + off) = make_float4(v[0], v[1], v[2], v[3]);
               if (kPasses == 3)
@@ -599,7 +601,7 @@ int fill_args(TcBwdArgs* a, int C, int H, int W, int P, int passes, int groups) 
     int gd_bytes = 0;
     if (md == 0) {
       m.raw_slots = a->n_gboxes;
-      m.gd_off = round_up(raw0, 1024);
+      m.gd_off = round_up(raw0 + 2 * kTM * 4, 1024);   // + the zero rows before plane 0 and after the last box
     } else {
       m.raw_slots = groups < 3 ? kMaxRawSlots1 : groups;   // 3 groups: 3 raw + 3 Gd slots fit, 4 + 3 do not
       m.gd_off = round_up(m.raw_slots * kRawSlot1, 1024);

@@ -4,6 +4,8 @@
 // one thread owns one (n,h,w), computes the two taps once and loops over channels.  Every fp32 step
 // of the reference (including the float32 flat gather index of torch_dsnet.py:59-70 and the
 // un-fused weight*pixel products) is reproduced, so the forward is bit-identical to the reference.
+#include <cub/block/block_radix_sort.cuh>
+
 #include "common.cuh"
 
 namespace pmt {
@@ -168,9 +170,11 @@ int warp_grid(int64_t total) {
 // While N*H*W < 2^24 the reference's float32 flat index is exact, so both taps of a pixel stay inside its own image row:
 // the scatter into gimg never leaves the row (n, h).  One CTA owns one row.  The tap structure -- which source pixels w
 // feed which destination x', with which weight -- does not depend on the channel, so it is built ONCE per row as a small
-// CSR in shared memory (count with integer atomics, exclusive scan, stable fill in increasing source order by one warp
-// with __match_any_sync), and every channel then GATHERS: gimg[c][x'] = sum over the bucket of x' of weight * g[c][w], in
-// bucket order.  No float atomics, every element of gimg written exactly once (no zero-fill launch), bit-reproducible run
+// CSR in shared memory (bucket sizes with integer atomics, exclusive scan, and a STABLE block radix sort of the
+// (destination, source) pairs -- cub::BlockRadixSort over the 2W taps -- so that every bucket lists its sources in
+// increasing order), and every channel then GATHERS: gimg[c][x'] = sum over the bucket of x' of weight * g[c][w], in
+// bucket order.  Buckets with more than kBigBucket entries (the clamped image borders collect dozens of taps) are summed
+// by a whole warp in a fixed lane-strided order + shuffle tree instead of by one thread.  No float atomics, every element of gimg written exactly once (no zero-fill launch), bit-reproducible run
 // to run.  The 8 warps of the CTA split the channels; each stages its g row (and image row, for goff) in shared memory
 // with coalesced loads.  goff = sum_c g * (img[x1] - img[x0]) is accumulated per warp in registers and combined across
 // warps in fixed order.
@@ -183,7 +187,12 @@ int warp_grid(int64_t total) {
 //                dsnet_t2_warp.py:811):  ge = mask * scale * (warp*mask - left), scale = 2*gloss/numel
 // ---------------------------------------------------------------------------------------------------------------------
 constexpr int kRowWarps = 8, kRowThreads = 32 * kRowWarps;
-constexpr int kMaxWPerLane = 32;   // W <= 1024: per-lane goff partials live in registers
+constexpr int kRowMaxW = 1024;                       // a thread owns pixels w = tid + 256 i, i < 4
+constexpr int kPerThread = kRowMaxW / kRowThreads;   // 4
+constexpr int kRowChunk = 8;                         // channels staged per pass
+constexpr int kBigBucket = 8;                        // buckets above this size are reduced by a warp
+constexpr int kMaxBig = 64;                          // big buckets per row handled by warps (more: the owning thread loops)
+using RowSort = cub::BlockRadixSort<unsigned int, kRowThreads, 2 * kPerThread, unsigned int>;
 
 struct RowBwdArgs {
   const float* img;      // (N,C,H,W) source image of the warp
@@ -191,7 +200,7 @@ struct RowBwdArgs {
   const float* gout;     // mode 0/1: upstream gradient; layout per gout_cnhw.  mode 2: unused
   const float* aux;      // mode 1: seg (N,C,H,W) the warp is blended with;  mode 2: left (N,C,H,W)
   const float* att;      // mode 1: (N,1,H,W) blend weight
-  const float* gwarp;    // mode 1: optional gradient w.r.t. the warped tensor itself (same layout as gout), may be null
+  const float* gwarp;    // mode 1: optional gradient w.r.t. the warped tensor itself (N,C,H,W), may be null
   float* gimg;           // (N,C,H,W) or null
   float* goff;           // (N,1,H,W) or null
   float* gaux;           // mode 1: gseg (N,C,H,W);  mode 2: gleft (N,C,H,W) or null
@@ -203,7 +212,7 @@ struct RowBwdArgs {
 };
 
 __device__ __forceinline__ int block_exclusive_scan(int v, int* warp_sums, int tid) {
-  // exclusive scan of one int per thread over the 256-thread CTA; returns the exclusive prefix, total in warp_sums[8]
+  // exclusive scan of one int per thread over the 256-thread CTA; returns the exclusive prefix, total in warp_sums[7]
   const int lane = tid & 31, wid = tid >> 5;
   int x = v;
 #pragma unroll
@@ -227,30 +236,48 @@ __device__ __forceinline__ int block_exclusive_scan(int v, int* warp_sums, int t
   return base + x - v;
 }
 
+// Shared-memory layout of one row's tap structure + the staged channel chunk (floats first, then ints, shorts, bytes).
+struct RowSmem {
+  float *twl, *twr, *ev, *gs, *is;
+  int *offs, *cur, *wsum, *big;
+  unsigned short *tx0, *tx1, *ew;
+  unsigned char* tpass;
+};
+__host__ __device__ inline size_t row_smem_layout(int W, unsigned char* base, RowSmem* r) {
+  const size_t W4 = (size_t)((W + 3) & ~3);
+  size_t o = 0;
+  auto take = [&](size_t bytes) { const size_t at = o; o += (bytes + 15) & ~(size_t)15; return at; };
+  const size_t o_twl = take(4 * W4), o_twr = take(4 * W4), o_ev = take(8 * W4),
+               // gs and is are contiguous; the region also hosts the radix sort's temporary storage (used before them)
+               o_gs = take(8 * kRowChunk * W4 > sizeof(RowSort::TempStorage) ? 8 * kRowChunk * W4 : sizeof(RowSort::TempStorage)),
+               o_is = o_gs + 4 * kRowChunk * W4, o_offs = take(4 * (W4 + 4)), o_cur = take(4 * W4), o_ws = take(64), o_big = take(4 * (kMaxBig + 4)),
+               o_x0 = take(2 * W4), o_x1 = take(2 * W4), o_ew = take(4 * W4), o_ps = take(W4);
+  if (r != nullptr) {
+    r->twl = reinterpret_cast<float*>(base + o_twl), r->twr = reinterpret_cast<float*>(base + o_twr);
+    r->ev = reinterpret_cast<float*>(base + o_ev), r->gs = reinterpret_cast<float*>(base + o_gs);
+    r->is = reinterpret_cast<float*>(base + o_is), r->offs = reinterpret_cast<int*>(base + o_offs);
+    r->cur = reinterpret_cast<int*>(base + o_cur), r->wsum = reinterpret_cast<int*>(base + o_ws);
+    r->big = reinterpret_cast<int*>(base + o_big);
+    r->tx0 = reinterpret_cast<unsigned short*>(base + o_x0), r->tx1 = reinterpret_cast<unsigned short*>(base + o_x1);
+    r->ew = reinterpret_cast<unsigned short*>(base + o_ew), r->tpass = base + o_ps;
+  }
+  return o;
+}
+
 template <int kMode>
 __global__ void __launch_bounds__(kRowThreads) warp_bwd_rows_kernel(const RowBwdArgs a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
+  RowSmem sm;
+  row_smem_layout(a.W, smem_raw, &sm);
   const int W = a.W, C = a.C;
-  // shared layout (all sizes multiples of 4 bytes): weights, taps, CSR, per-warp rows
-  float* twl = reinterpret_cast<float*>(smem_raw);
-  float* twr = twl + W;
-  float* ev = twr + W;                                   // [2W] bucket weights
-  int* offs = reinterpret_cast<int*>(ev + 2 * W);        // [W+1] bucket starts
-  int* cur = offs + (W + 1);                             // [W] counts, then fill cursors
-  int* wsum = cur + W;                                   // [8] scan scratch
-  unsigned short* tx0 = reinterpret_cast<unsigned short*>(wsum + 8);
-  unsigned short* tx1 = tx0 + W;
-  unsigned short* ew = tx1 + W;                          // [2W] bucket sources
-  unsigned char* tpass = reinterpret_cast<unsigned char*>(ew + 2 * W);   // [W]
   const int W4 = (W + 3) & ~3;
-  float* rows = reinterpret_cast<float*>(smem_raw + (((size_t)(4 * W + (2 * W + 9)) * 4 + (size_t)4 * W * 2 + W + 15) & ~(size_t)15));
   const int tid = threadIdx.x, wid = tid >> 5, lane = tid & 31;
-  float* gs = rows + (size_t)wid * 3 * W4;               // staged effective gradient row of this warp's channel
-  float* is = gs + W4;                                   // staged image row
-  float* xs = is + W4;                                   // mode 1: att row / mode 2: unused (per warp copy keeps it simple)
   const int64_t plane = (int64_t)a.H * W, total = (int64_t)a.N * plane;
   const bool need_img = a.gimg != nullptr;
-  const bool need_is = a.goff != nullptr || kMode != 0;   // the image row is needed for goff and to recompute the warp
+  const bool need_is = a.goff != nullptr || kMode != 0;   // the image rows are needed for goff and to recompute the warp
+  const float sc = kMode == 2 ? a.scale * (a.gloss != nullptr ? __ldg(a.gloss) : 1.f) : 0.f;
+  // 16-byte copies need 16-byte aligned row starts in global memory
+  const bool vec16 = (W & 3) == 0 && ((reinterpret_cast<uintptr_t>(a.img) | reinterpret_cast<uintptr_t>(a.gout)) & 15) == 0;
 
   for (int row = blockIdx.x; row < a.N * a.H; row += gridDim.x) {
     const int n = row / a.H, h = row % a.H;
@@ -258,18 +285,17 @@ __global__ void __launch_bounds__(kRowThreads) warp_bwd_rows_kernel(const RowBwd
     // ---- A. taps of every pixel of the row ----
     for (int w = tid; w < W; w += kRowThreads) {
       const Taps t = make_taps(n, h, w, __ldg(a.off + roff + w), a.H, W, total);
-      const int x0 = (int)(t.il - roff), x1 = (int)(t.ir - roff);     // exact below 2^24: 0 <= x0 <= x1 <= W-1
-      tx0[w] = (unsigned short)x0, tx1[w] = (unsigned short)x1;
-      twl[w] = t.wl, twr[w] = t.wr;
-      tpass[w] = t.pass ? 1 : 0;
-      cur[w] = 0;
+      sm.tx0[w] = (unsigned short)(t.il - roff), sm.tx1[w] = (unsigned short)(t.ir - roff);   // exact below 2^24
+      sm.twl[w] = t.wl, sm.twr[w] = t.wr;
+      sm.tpass[w] = t.pass ? 1 : 0;
+      sm.cur[w] = 0;
     }
     __syncthreads();
     if (need_img) {
       // ---- B. bucket sizes (integer atomics: deterministic) ----
       for (int w = tid; w < W; w += kRowThreads) {
-        if (twl[w] != 0.f) atomicAdd(&cur[tx0[w]], 1);
-        if (twr[w] != 0.f) atomicAdd(&cur[tx1[w]], 1);
+        if (sm.twl[w] != 0.f) atomicAdd(&sm.cur[sm.tx0[w]], 1);
+        if (sm.twr[w] != 0.f) atomicAdd(&sm.cur[sm.tx1[w]], 1);
       }
       __syncthreads();
       // ---- C. exclusive scan -> bucket starts ----
@@ -278,151 +304,192 @@ __global__ void __launch_bounds__(kRowThreads) warp_bwd_rows_kernel(const RowBwd
         const int b0 = tid * per;
         int local = 0;
         for (int i = 0; i < per; ++i)
-          if (b0 + i < W) local += cur[b0 + i];
-        int run = block_exclusive_scan(local, wsum, tid);
+          if (b0 + i < W) local += sm.cur[b0 + i];
+        int run = block_exclusive_scan(local, sm.wsum, tid);
         for (int i = 0; i < per; ++i)
           if (b0 + i < W) {
-            const int c = cur[b0 + i];
-            offs[b0 + i] = run;
-            cur[b0 + i] = run;
+            const int c = sm.cur[b0 + i];
+            sm.offs[b0 + i] = run;
+            sm.cur[b0 + i] = run;
             run += c;
           }
-        if (tid == kRowThreads - 1) offs[W] = wsum[kRowWarps - 1];
+        if (tid == kRowThreads - 1) sm.offs[W] = sm.wsum[kRowWarps - 1];
       }
       __syncthreads();
-      // ---- D. stable fill by warp 0: bucket entries in increasing (32-pixel chunk, tap kind, lane) order ----
-      if (wid == 0) {
-        for (int base = 0; base < W; base += 32) {
-          const int w = base + lane;
+      // ---- D. stable sort of the taps by destination: entries of bucket k land in [offs[k], offs[k+1]) in increasing
+      // (source pixel, tap kind) order.  Thread t owns pixels 4t..4t+3 (blocked arrangement = source order). ----
+      {
+        typename RowSort::TempStorage& tmp = *reinterpret_cast<typename RowSort::TempStorage*>(sm.gs);   // gs/is are free here
+        unsigned int keys[2 * kPerThread], vals[2 * kPerThread];
 #pragma unroll
-          for (int kind = 0; kind < 2; ++kind) {
-            const float wt = w < W ? (kind ? twr[w] : twl[w]) : 0.f;
-            const int key = w < W ? (int)(kind ? tx1[w] : tx0[w]) : 0;
-            const bool valid = wt != 0.f;
-            const unsigned vm = __ballot_sync(0xffffffffu, valid);
-            int pos = 0;
-            unsigned m = 0;
-            if (valid) {
-              m = __match_any_sync(vm, key);
-              pos = cur[key] + __popc(m & ((1u << lane) - 1u));
-            }
-            __syncwarp();
-            if (valid && lane == __ffs(m) - 1) cur[key] += __popc(m);
-            if (valid) {
-              ew[pos] = (unsigned short)w;
-              ev[pos] = wt;
-            }
-            __syncwarp();
+        for (int i = 0; i < kPerThread; ++i) {
+          const int w = kPerThread * tid + i;
+          const bool in = w < W;
+          const float wl = in ? sm.twl[w] : 0.f, wr = in ? sm.twr[w] : 0.f;
+          keys[2 * i] = wl != 0.f ? (unsigned)sm.tx0[w] : 0x7ffu;        // taps without weight sort behind every bucket
+          keys[2 * i + 1] = wr != 0.f ? (unsigned)sm.tx1[w] : 0x7ffu;
+          vals[2 * i] = (unsigned)(2 * w), vals[2 * i + 1] = (unsigned)(2 * w + 1);
+        }
+        RowSort(tmp).Sort(keys, vals, 0, 11);
+        const int n_entries = sm.offs[W];
+#pragma unroll
+        for (int i = 0; i < 2 * kPerThread; ++i) {
+          const int pos = 2 * kPerThread * tid + i;
+          if (pos < n_entries) {
+            const int w = (int)(vals[i] >> 1);
+            sm.ew[pos] = (unsigned short)w;
+            sm.ev[pos] = (vals[i] & 1u) ? sm.twr[w] : sm.twl[w];
           }
         }
+        // big buckets -> list for the warp-cooperative pass (list order is irrelevant: every bucket is summed on its own)
+        if (tid == 0) sm.big[kMaxBig] = 0;
+        __syncthreads();
+        for (int x = tid; x < W; x += kRowThreads)
+          if (sm.offs[x + 1] - sm.offs[x] > kBigBucket) {
+            const int slot = atomicAdd(&sm.big[kMaxBig], 1);
+            if (slot < kMaxBig) sm.big[slot] = x;
+          }
       }
       __syncthreads();
     }
-    // ---- E. channels: warp `wid` takes c = wid, wid+8, ... ----
-    const float sc = kMode == 2 ? a.scale * (a.gloss != nullptr ? __ldg(a.gloss) : 1.f) : 0.f;
-    float dgo[kMaxWPerLane];    // goff partial of pixel w = lane + 32 i
-    float dga[kMode == 1 ? kMaxWPerLane : 1];   // gatt partial
+    // ---- E. channel chunks: all 256 threads stage kRowChunk rows, then thread t owns pixels / destinations t + 256 i ----
+    float dgo[kPerThread], dga[kPerThread];
+    int b_[kPerThread], n_[kPerThread];
 #pragma unroll
-    for (int i = 0; i < kMaxWPerLane; ++i) dgo[i] = 0.f;
-    if (kMode == 1) {
-#pragma unroll
-      for (int i = 0; i < (kMode == 1 ? kMaxWPerLane : 1); ++i) dga[i] = 0.f;
-      for (int w = lane; w < W; w += 32) xs[w] = __ldg(a.att + roff + w);
+    for (int i = 0; i < kPerThread; ++i) {
+      dgo[i] = 0.f, dga[i] = 0.f;
+      const int x = tid + kRowThreads * i;
+      b_[i] = (need_img && x < W) ? sm.offs[x] : 0;
+      n_[i] = (need_img && x < W) ? sm.offs[x + 1] - b_[i] : 0;
     }
-    for (int c = wid; c < C; c += kRowWarps) {
-      const int64_t coff = ((int64_t)n * C + c) * plane + (int64_t)h * W;     // row inside an (N,C,H,W) tensor
-      const int64_t goff_ = a.gout_cnhw ? (int64_t)c * total + roff : coff;   // row inside gout / gwarp
-      if (need_is)
-        for (int w = lane; w < W; w += 32) is[w] = __ldg(a.img + coff + w);
-      if (kMode == 0)
-        for (int w = lane; w < W; w += 32) gs[w] = __ldg(a.gout + goff_ + w);
-      __syncwarp();
-      if (kMode == 1) {
-        // blend: recompute the warp, split the upstream gradient
+    const int n_big_all = need_img ? sm.big[kMaxBig] : 0;
+    const int n_big = n_big_all < kMaxBig ? n_big_all : kMaxBig;
+    const bool warps_take_big = n_big_all <= kMaxBig;     // otherwise (pathological) the owning threads loop themselves
+    for (int c0 = 0; c0 < C; c0 += kRowChunk) {
+      const int nc = C - c0 < kRowChunk ? C - c0 : kRowChunk;
+      // stage the chunk's rows with cp.async: every copy of the chunk is in flight before the first one is waited for
+      // (a load -> store loop left one or two loads per thread in flight and made the kernel latency-bound)
+      {
+        const int64_t crow = ((int64_t)n * C + c0) * plane + (int64_t)h * W;    // row of channel c0 in an (N,C,H,W) tensor
+        const int64_t grow = a.gout_cnhw ? (int64_t)c0 * total + roff : crow;    // ... in gout
+        const int64_t gstep = a.gout_cnhw ? total : plane;
+        if (vec16) {
+          const int Wq = W >> 2;
+          for (int i = tid; i < nc * Wq; i += kRowThreads) {
+            const int cc = i / Wq, q = i - cc * Wq;
+            if (need_is) cp_async16(sm.is + cc * W4 + 4 * q, a.img + crow + (int64_t)cc * plane + 4 * q, true);
+            if (kMode == 0) cp_async16(sm.gs + cc * W4 + 4 * q, a.gout + grow + (int64_t)cc * gstep + 4 * q, true);
+          }
+        } else {
+          for (int i = tid; i < nc * W; i += kRowThreads) {
+            const int cc = i / W, w = i - cc * W;
+            if (need_is) cp_async4(sm.is + cc * W4 + w, a.img + crow + (int64_t)cc * plane + w);
+            if (kMode == 0) cp_async4(sm.gs + cc * W4 + w, a.gout + grow + (int64_t)cc * gstep + w);
+          }
+        }
+        cp_async_commit();
+        cp_async_wait<0>();
+      }
+      __syncthreads();
+      if (kMode != 0) {
+        // recompute the warp, derive the effective upstream gradient of the warped tensor and the consumer's own
+        // gradients.  The global operands of the thread's pixels x channels are fetched first (independent loads).
 #pragma unroll
-        for (int i = 0; i < kMaxWPerLane; ++i) {
-          const int w = lane + 32 * i;
+        for (int i = 0; i < kPerThread; ++i) {
+          const int w = tid + kRowThreads * i;
           if (w < W) {
-            const float g = __ldg(a.gout + goff_ + w), at = xs[w];
-            const float wv = __fadd_rn(__fmul_rn(twl[w], is[tx0[w]]), __fmul_rn(twr[w], is[tx1[w]]));
-            const float sv = __ldg(a.aux + coff + w);
-            dga[i] = fmaf(g, wv - sv, dga[i]);
-            a.gaux[coff + w] = (1.f - at) * g;
-            float ge = at * g;
-            if (a.gwarp != nullptr) ge += __ldg(a.gwarp + goff_ + w);
-            gs[w] = ge;
+            const int x0 = sm.tx0[w], x1 = sm.tx1[w];
+            const float wl = sm.twl[w], wr = sm.twr[w];
+            const float at = kMode == 1 ? __ldg(a.att + roff + w) : 0.f;
+            const float mk = (kMode == 2 && a.mask_pos && !(__ldg(a.off + roff + w) < 0.f)) ? 0.f : 1.f;
+            const int64_t c00 = ((int64_t)n * C + c0) * plane + (int64_t)h * W + w;
+            float gq[kRowChunk], aq[kRowChunk], wq[kRowChunk];
+#pragma unroll
+            for (int cc = 0; cc < kRowChunk; ++cc) {
+              const bool ok = cc < nc;
+              aq[cc] = ok ? __ldg(a.aux + c00 + (int64_t)cc * plane) : 0.f;
+              gq[cc] = (ok && kMode == 1) ? __ldg(a.gout + c00 + (int64_t)cc * plane) : 0.f;
+              wq[cc] = (ok && kMode == 1 && a.gwarp != nullptr) ? __ldg(a.gwarp + c00 + (int64_t)cc * plane) : 0.f;
+            }
+#pragma unroll
+            for (int cc = 0; cc < kRowChunk; ++cc) {
+              if (cc < nc) {
+                const int64_t coff = c00 + (int64_t)cc * plane;
+                const float wv = __fadd_rn(__fmul_rn(wl, sm.is[cc * W4 + x0]), __fmul_rn(wr, sm.is[cc * W4 + x1]));
+                float ge;
+                if (kMode == 1) {
+                  dga[i] = fmaf(gq[cc], wv - aq[cc], dga[i]);
+                  a.gaux[coff] = (1.f - at) * gq[cc];
+                  ge = at * gq[cc] + wq[cc];
+                } else {
+                  const float d = sc * (wv * mk - aq[cc]);
+                  if (a.gaux != nullptr) a.gaux[coff] = -d;
+                  ge = mk * d;
+                }
+                sm.gs[cc * W4 + w] = ge;
+              }
+            }
           }
         }
-        __syncwarp();
-      } else if (kMode == 2) {
+        __syncthreads();
+      }
 #pragma unroll
-        for (int i = 0; i < kMaxWPerLane; ++i) {
-          const int w = lane + 32 * i;
-          if (w < W) {
-            float wv = __fadd_rn(__fmul_rn(twl[w], is[tx0[w]]), __fmul_rn(twr[w], is[tx1[w]]));
-            const float mk = (a.mask_pos && !(__ldg(a.off + roff + w) < 0.f)) ? 0.f : 1.f;
-            wv *= mk;
-            const float d = sc * (wv - __ldg(a.aux + coff + w));
-            if (a.gaux != nullptr) a.gaux[coff + w] = -d;
-            gs[w] = mk * d;
+      for (int i = 0; i < kPerThread; ++i) {
+        const int x = tid + kRowThreads * i;
+        if (x < W) {
+          if (a.goff != nullptr) {
+            const int x0 = sm.tx0[x], x1 = sm.tx1[x];
+            for (int cc = 0; cc < nc; ++cc) dgo[i] = fmaf(sm.gs[cc * W4 + x], sm.is[cc * W4 + x1] - sm.is[cc * W4 + x0], dgo[i]);
+          }
+          if (need_img && !(warps_take_big && n_[i] > kBigBucket)) {
+            // bucket of destination x: entries b .. b+n-1; the first two inline, the (rare) rest in a loop
+            const int b = b_[i], nb = n_[i];
+            const float v0 = nb > 0 ? sm.ev[b] : 0.f, v1 = nb > 1 ? sm.ev[b + 1] : 0.f;
+            const int w0 = nb > 0 ? sm.ew[b] : 0, w1 = nb > 1 ? sm.ew[b + 1] : 0;
+            for (int cc = 0; cc < nc; ++cc) {
+              const float* g = sm.gs + cc * W4;
+              float acc = __fadd_rn(__fmul_rn(v0, g[w0]), __fmul_rn(v1, g[w1]));
+              for (int e = b + 2; e < b + nb; ++e) acc = __fadd_rn(acc, __fmul_rn(sm.ev[e], g[sm.ew[e]]));
+              st_cs(a.gimg + ((int64_t)n * C + c0 + cc) * plane + (int64_t)h * W + x, acc);
+            }
           }
         }
-        __syncwarp();
       }
-      if (a.goff != nullptr) {
+      if (need_img && warps_take_big) {
+        // big buckets: warp `wid` takes buckets wid, wid+8, ...; lane l adds entries b+l, b+l+32, ... in order, then a
+        // fixed shuffle tree -> the same order every run
+        for (int j = wid; j < n_big; j += kRowWarps) {
+          const int x = sm.big[j], b = sm.offs[x], nb = sm.offs[x + 1] - b;
+          for (int cc = 0; cc < nc; ++cc) {
+            const float* g = sm.gs + cc * W4;
+            float acc = 0.f;
+            for (int e = b + lane; e < b + nb; e += 32) acc = __fadd_rn(acc, __fmul_rn(sm.ev[e], g[sm.ew[e]]));
 #pragma unroll
-        for (int i = 0; i < kMaxWPerLane; ++i) {
-          const int w = lane + 32 * i;
-          if (w < W) dgo[i] = fmaf(gs[w], is[tx1[w]] - is[tx0[w]], dgo[i]);
+            for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+            if (lane == 0) a.gimg[((int64_t)n * C + c0 + cc) * plane + (int64_t)h * W + x] = acc;
+          }
         }
       }
-      if (need_img) {
-        float* o = a.gimg + coff;
-        for (int x = lane; x < W; x += 32) {
-          float acc = 0.f;
-          const int e1 = offs[x + 1];
-          for (int e = offs[x]; e < e1; ++e) acc = __fadd_rn(acc, __fmul_rn(ev[e], gs[ew[e]]));
-          st_cs(o + x, acc);
-        }
-      }
-      __syncwarp();   // gs / is are overwritten by the next channel
+      __syncthreads();   // gs / is are overwritten by the next chunk
     }
-    // ---- F. combine the per-warp goff / gatt partials in fixed order ----
-    __syncthreads();
-    if (a.goff != nullptr || kMode == 1) {
+    // ---- F. per-pixel results ----
 #pragma unroll
-      for (int i = 0; i < kMaxWPerLane; ++i) {
-        const int w = lane + 32 * i;
-        if (w < W) {
-          gs[w] = dgo[i];
-          if (kMode == 1) is[w] = dga[i];
-        }
-      }
-      __syncthreads();
-      for (int w = tid; w < W; w += kRowThreads) {
-        float s = 0.f, s2 = 0.f;
-#pragma unroll
-        for (int k = 0; k < kRowWarps; ++k) {
-          s += rows[(size_t)k * 3 * W4 + w];
-          if (kMode == 1) s2 += rows[(size_t)k * 3 * W4 + W4 + w];
-        }
-        if (a.goff != nullptr) a.goff[roff + w] = tpass[w] ? s : 0.f;
-        if (kMode == 1) a.gatt[roff + w] = s2;
+    for (int i = 0; i < kPerThread; ++i) {
+      const int w = tid + kRowThreads * i;
+      if (w < W) {
+        if (a.goff != nullptr) a.goff[roff + w] = sm.tpass[w] ? dgo[i] : 0.f;
+        if (kMode == 1) a.gatt[roff + w] = dga[i];
       }
     }
     __syncthreads();   // shared memory is reused by the next row
   }
 }
 
-size_t rows_smem_bytes(int W) {
-  const int W4 = (W + 3) & ~3;
-  const size_t head = (((size_t)(4 * W + (2 * W + 9)) * 4 + (size_t)4 * W * 2 + W + 15) & ~(size_t)15);
-  return head + (size_t)kRowWarps * 3 * W4 * 4;
-}
+size_t rows_smem_bytes(int W) { return row_smem_layout(W, nullptr, nullptr); }
 
 // The row kernel needs exact float32 flat indices (taps inside the row) and W <= 1024 (register partials).
 bool rows_ok(int N, int H, int W) {
-  return (int64_t)N * H * W < (1ll << 24) && W <= 32 * kMaxWPerLane && W < 65536 && rows_smem_bytes(W) <= 200 * 1024;
+  return (int64_t)N * H * W < (1ll << 24) && W <= kRowMaxW && rows_smem_bytes(W) <= 200 * 1024;
 }
 
 template <int kMode>

@@ -136,6 +136,161 @@ class _PairedSyncBNFusedFn(torch.autograd.Function):
         return dx, gw, gb, None, None, None, None, None, None, None
 
 
+class PeerExchange:
+    """NVLink peer-memory exchange of the BN statistics of every PairedSyncBatchNorm layer of a model (csrc/bn_pair.cu,
+    include/pmt_ops.h `pmt_bn_pair_*_peer_f32`): one symmetric buffer per rank, mapped into every peer, holds for each
+    layer and direction a payload region [2 parity][world][n] and a flag region [2][world]; the kernels push their
+    payload into every peer's copy and spin on their own flags, so no collective is launched on the dependency chain
+    (DDP's gradient all-reduce stays with NCCL).
+
+    `PeerExchange.attach(module, group)` allocates the buffer with torch.distributed._symmetric_memory, assigns every
+    PairedSyncBatchNorm below `module` its offsets and switches those layers to the peer kernels.
+    `PeerExchange.emulated(world, ...)` builds `world` plain buffers on ONE device (tests: the ranks run one after the
+    other, so the consumers never have to wait)."""
+
+    def __init__(self, world, rank, local, ptr_table, keepalive=()):
+        self.world, self.rank = int(world), int(rank)
+        self.local = local                      # this rank's buffer (float32, flat)
+        self.ptr_table = ptr_table              # int64 device tensor [world]: base pointers of all ranks' buffers
+        self._keepalive = keepalive
+        self.cursor = 0                         # floats handed out so far (identical on all ranks)
+        dev = local.device
+        self.err = torch.zeros(1, dtype=torch.int32, device=dev)
+        self._counters = []
+
+    # ---- layout ----
+    @staticmethod
+    def floats_needed(module: nn.Module, world: int) -> int:
+        total = 0
+        for m in module.modules():
+            if isinstance(m, PairedSyncBatchNorm):
+                c = m.num_features
+                for n in (4 * c + 1, 4 * c):
+                    total += _round4(2 * world * n) + _round4(2 * world)
+        return total
+
+    def reserve(self, n: int):
+        """(payload_off, flag_off, epoch, done) for one layer+direction with `n` payload floats per rank."""
+        payload_off = self.cursor
+        self.cursor += _round4(2 * self.world * n)
+        flag_off = self.cursor
+        self.cursor += _round4(2 * self.world)
+        if self.cursor > self.local.numel():
+            raise RuntimeError("PeerExchange buffer too small")
+        counters = torch.zeros(2, dtype=torch.int32, device=self.local.device)   # [epoch, done]
+        self._counters.append(counters)
+        return payload_off, flag_off, counters
+
+    # ---- construction ----
+    @classmethod
+    def attach(cls, module: nn.Module, group=None):
+        import torch.distributed as dist
+        import torch.distributed._symmetric_memory as symm
+
+        group = group if group is not None else dist.group.WORLD
+        world, rank = dist.get_world_size(group), dist.get_rank(group)
+        dev = torch.device("cuda", torch.cuda.current_device())
+        n = max(cls.floats_needed(module, world), 4)
+        buf = symm.empty(n, dtype=torch.float32, device=dev)
+        buf.zero_()
+        hdl = symm.rendezvous(buf, group)
+        torch.cuda.synchronize(dev)
+        hdl.barrier()                            # every rank's flags are zero before anyone publishes
+        table = torch.tensor([int(p) for p in hdl.buffer_ptrs], dtype=torch.int64, device=dev)
+        self = cls(world, rank, buf, table, keepalive=(hdl,))
+        self._bind(module, group)
+        return self
+
+    @classmethod
+    def emulated(cls, world: int, floats: int, device):
+        bufs = [torch.zeros(max(floats, 4), dtype=torch.float32, device=device) for _ in range(world)]
+        table = torch.tensor([b.data_ptr() for b in bufs], dtype=torch.int64, device=device)
+        return [cls(world, r, bufs[r], table, keepalive=tuple(bufs)) for r in range(world)]
+
+    def _bind(self, module: nn.Module, group):
+        for m in module.modules():
+            if isinstance(m, PairedSyncBatchNorm):
+                c = m.num_features
+                m.peer = (self, self.reserve(4 * c + 1), self.reserve(4 * c))
+                m.process_group = group
+
+    def check(self):
+        """Raise if a kernel gave up waiting for a peer (reads one device word: call outside the hot loop)."""
+        if int(self.err.item()) != 0:
+            raise RuntimeError("PeerExchange: a batch-norm kernel waited > 2 s for the statistics of a peer rank")
+
+
+def _round4(n: int) -> int:
+    return (int(n) + 3) & ~3
+
+
+class _PairedSyncBNPeerFn(torch.autograd.Function):
+    """_PairedSyncBNFusedFn with the exchange done inside the kernels over NVLink peer memory (no collective launch)."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, running_mean, running_var, eps, momentum, peer, relu=False):
+        import ctypes
+
+        from . import _util as U
+
+        xch, (f_pay, f_flag, f_cnt), bwd = peer
+        x = x.contiguous()
+        B2, C = x.size(0), x.size(1)
+        B, HW = B2 // 2, x[0, 0].numel()
+        dev = x.device
+        lib = U._lib.load()
+        vp = ctypes.c_void_p
+        with torch.cuda.device(dev):
+            st = lib.pmt_bn_pair_stats_peer_f32(U.ptr(x), vp(xch.ptr_table.data_ptr()), vp(xch.local.data_ptr()), xch.world,
+                                                xch.rank, f_pay, f_flag, vp(f_cnt.data_ptr()), vp(f_cnt.data_ptr() + 4),
+                                                vp(xch.err.data_ptr()), B, C, HW, U.stream_ptr(dev))
+            U._lib.check(st, "pmt_bn_pair_stats_peer_f32")
+            out = torch.empty_like(x)
+            save_mean = torch.empty(2 * C, device=dev, dtype=torch.float32)
+            save_invstd = torch.empty(2 * C + 1, device=dev, dtype=torch.float32)   # [2C] = total count
+            st = lib.pmt_bn_pair_apply_peer_f32(U.ptr(x), vp(xch.local.data_ptr()), xch.world, f_pay, f_flag,
+                                                vp(f_cnt.data_ptr()), vp(xch.err.data_ptr()), U.ptr(weight), U.ptr(bias),
+                                                U.ptr(running_mean), U.ptr(running_var), ctypes.c_float(momentum),
+                                                ctypes.c_float(eps), U.ptr(out), U.ptr(save_mean), U.ptr(save_invstd), B, C,
+                                                HW, int(bool(relu)), U.stream_ptr(dev))
+            U._lib.check(st, "pmt_bn_pair_apply_peer_f32")
+        ctx.save_for_backward(x, weight, bias, save_mean, save_invstd)
+        ctx.peer, ctx.relu = (xch, bwd), int(bool(relu))
+        return out
+
+    @staticmethod
+    def backward(ctx, grad):
+        import ctypes
+
+        from . import _util as U
+
+        x, weight, bias, save_mean, save_invstd = ctx.saved_tensors
+        xch, (b_pay, b_flag, b_cnt) = ctx.peer
+        grad = grad.contiguous()
+        B2, C = x.size(0), x.size(1)
+        B, HW = B2 // 2, x[0, 0].numel()
+        dev = x.device
+        lib = U._lib.load()
+        vp = ctypes.c_void_p
+        gwb = torch.zeros(2, C, device=dev, dtype=torch.float32)
+        dx = torch.empty_like(x)
+        with torch.cuda.device(dev):
+            st = lib.pmt_bn_pair_bwd_reduce_peer_f32(U.ptr(grad), U.ptr(x), U.ptr(save_mean), U.ptr(save_invstd),
+                                                     vp(xch.ptr_table.data_ptr()), vp(xch.local.data_ptr()), xch.world, xch.rank,
+                                                     b_pay, b_flag, vp(b_cnt.data_ptr()), vp(b_cnt.data_ptr() + 4),
+                                                     vp(xch.err.data_ptr()), U.ptr(gwb[0]), U.ptr(gwb[1]), B, C, HW,
+                                                     U.ptr(weight), U.ptr(bias), ctx.relu, U.stream_ptr(dev))
+            U._lib.check(st, "pmt_bn_pair_bwd_reduce_peer_f32")
+            st = lib.pmt_bn_pair_bwd_apply_peer_f32(U.ptr(grad), U.ptr(x), U.ptr(save_mean), U.ptr(save_invstd), U.ptr(weight),
+                                                    vp(xch.local.data_ptr()), xch.world, b_pay, b_flag, vp(b_cnt.data_ptr()),
+                                                    vp(xch.err.data_ptr()), U.ptr(dx), B, C, HW, U.ptr(bias), ctx.relu,
+                                                    U.stream_ptr(dev))
+            U._lib.check(st, "pmt_bn_pair_bwd_apply_peer_f32")
+        gw = gwb[0] if weight is not None else None
+        gb = gwb[1] if weight is not None else None
+        return dx, gw, gb, None, None, None, None, None, None
+
+
 class PairedSyncBatchNorm(nn.BatchNorm2d):
     """Drop-in for the BatchNorm2d / SyncBatchNorm layers of a siamese tower that is fed [left; right] in one pass (see
     _PairedSyncBNFn).  Single process: equals calling the BatchNorm2d on each half in turn.
@@ -148,6 +303,7 @@ class PairedSyncBatchNorm(nn.BatchNorm2d):
     fused = True
     relu = False   # True: the ReLU that follows this BN is computed by the same kernels (pair_batchnorms sets it)
     process_group = None
+    peer = None    # (PeerExchange, forward slot, backward slot): statistics travel over NVLink peer memory, no collective
 
     def _world(self):
         dist = torch.distributed
@@ -177,6 +333,10 @@ class PairedSyncBatchNorm(nn.BatchNorm2d):
                 self.num_batches_tracked.add_(2)
             if x.data_ptr() % 16:
                 x = x.clone(memory_format=torch.contiguous_format)   # an offset view: the kernels read 16-byte vectors
+            if self.peer is not None:
+                return _PairedSyncBNPeerFn.apply(x, self.weight, self.bias, self.running_mean if track else None,
+                                                 self.running_var if track else None, self.eps,
+                                                 self.momentum if self.momentum is not None else 0.0, self.peer, self.relu)
             return _PairedSyncBNFusedFn.apply(x, self.weight, self.bias, self.running_mean if track else None,
                                               self.running_var if track else None, self.eps,
                                               self.momentum if self.momentum is not None else 0.0, self.process_group, ws,

@@ -266,3 +266,17 @@ def test_corr_fp64_restatement_bound(pmt):
                                              patch_size=(1, P)))
     assert rel_err(out, ref64) <= FP32_TOL
     assert rel_err(oracle.corr_fwd(L, R, patch_size=(1, P)), ref64) <= FP32_TOL
+
+
+@pytest.mark.parametrize("B,C,H,W,pH", [(2, 352, 32, 64, 17), (1, 40, 5, 120, 17), (1, 8, 20, 16, 5)])
+def test_corr2d_row_pass_kernels_vs_oracle(pmt, B, C, H, W, pH):
+    """f3: (pH,17) patches run as row-pair passes through shared memory (csrc/corr2d_rows.cu), incl. the full
+    `-corrType 2dcorr` call of the reference (patch (17,17), C=352, 32x64: models/dsnet_t2.py:129-133,221-223)."""
+    rng = np.random.default_rng(C + W + pH)
+    L = rng.standard_normal((B, C, H, W), dtype=np.float32)
+    R = rng.standard_normal((B, C, H, W), dtype=np.float32)
+    G = rng.standard_normal((B, pH, 17, H, W), dtype=np.float32)
+    out, g1, g2 = run_corr(pmt, L, R, G, (pH, 17))
+    ref = oracle.corr_fwd(L, R, patch_size=(pH, 17))
+    r1, r2 = oracle.corr_bwd(L, R, G, patch_size=(pH, 17))
+    assert rel_err(out, ref) <= FP32_TOL and rel_err(g1, r1) <= FP32_TOL and rel_err(g2, r2) <= FP32_TOL

@@ -180,3 +180,89 @@ def test_bn_pair_multi_rank_combine_on_one_gpu():
     gw, gb = gws[0][0] + gws[1][0], gws[0][1] + gws[1][1]
     assert float((gw.double() - ref_bn.weight.grad).abs().max()) <= 1e-4 * float(ref_bn.weight.grad.abs().max())
     assert float((gb.double() - ref_bn.bias.grad).abs().max()) <= 1e-4 * float(ref_bn.bias.grad.abs().max())
+
+
+def test_bn_pair_peer_exchange_emulated_two_ranks():
+    """The NVLink peer-memory exchange of the bn_pair kernels (pmt_bn_pair_*_peer_f32) on ONE GPU: two emulated ranks,
+    each with its own buffer, run one after the other (so no consumer ever has to wait).  Producers push their payload
+    into BOTH buffers and publish an epoch; consumers read their own buffer.  Results must equal the collective path
+    (payloads exchanged by hand) bit for bit, for two consecutive steps (the slots are double-buffered by epoch parity)."""
+    import ctypes
+
+    from pmt_learning_for_semantic_segmentation_and_disparity_b200 import PeerExchange
+    from pmt_learning_for_semantic_segmentation_and_disparity_b200 import _util as U
+
+    DEV = torch.device("cuda:0")
+    torch.manual_seed(5)
+    B, C, H, W, world, eps, mom = 2, 6, 10, 12, 2, 1e-5, 0.1
+    HW = H * W
+    lib = U._lib.load()
+    vp = ctypes.c_void_p
+    ranks = PeerExchange.emulated(world, 4 * (2 * world * (4 * C + 1) + 2 * world * 4 * C + 64), DEV)
+    slots = [(x.reserve(4 * C + 1), x.reserve(4 * C)) for x in ranks]
+    weight, bias = torch.rand(C, device=DEV) + 0.5, torch.randn(C, device=DEV)
+    for step in range(3):
+        xs = [(2.0 * torch.randn(2 * B, C, H, W, device=DEV) + r + step) for r in range(world)]
+        dys = [torch.randn(2 * B, C, H, W, device=DEV) for _ in range(world)]
+        # ---- collective path (reference): payloads exchanged by hand ----
+        gathered = torch.empty(world, 4 * C + 1, device=DEV)
+        for r in range(world):
+            U.call("pmt_bn_pair_stats_f32", DEV, U.ptr(xs[r]), U.ptr(gathered[r]), B, C, HW)
+        want = []
+        for r in range(world):
+            out, sm, si = torch.empty_like(xs[r]), torch.empty(2 * C, device=DEV), torch.empty(2 * C + 1, device=DEV)
+            st = lib.pmt_bn_pair_apply_f32(U.ptr(xs[r]), U.ptr(gathered), world, U.ptr(weight), U.ptr(bias), None, None,
+                                           ctypes.c_float(mom), ctypes.c_float(eps), U.ptr(out), U.ptr(sm), U.ptr(si), B, C, HW,
+                                           1, U.stream_ptr(DEV))
+            assert st == 0
+            sums, gw = torch.empty(4 * C, device=DEV), torch.zeros(2, C, device=DEV)
+            U.call("pmt_bn_pair_bwd_reduce_f32", DEV, U.ptr(dys[r]), U.ptr(xs[r]), U.ptr(sm), U.ptr(si), U.ptr(sums),
+                   U.ptr(gw[0]), U.ptr(gw[1]), B, C, HW, U.ptr(weight), U.ptr(bias), 1)
+            want.append([out, sm, si, sums, None])
+        total = want[0][3] + want[1][3]                       # rank order 0 + 1, as the peer consumer adds them
+        for r in range(world):
+            dx = torch.empty_like(xs[r])
+            U.call("pmt_bn_pair_bwd_apply_f32", DEV, U.ptr(dys[r]), U.ptr(xs[r]), U.ptr(want[r][1]), U.ptr(want[r][2]),
+                   U.ptr(weight), U.ptr(total), U.ptr(dx), B, C, HW, U.ptr(bias), 1)
+            want[r][4] = dx
+        # ---- peer path: every producer first (all payloads land in both buffers), then the consumers ----
+        got = [[None] * 5 for _ in range(world)]
+        for r, xch in enumerate(ranks):
+            (f_pay, f_flag, f_cnt), _ = slots[r]
+            st = lib.pmt_bn_pair_stats_peer_f32(U.ptr(xs[r]), vp(xch.ptr_table.data_ptr()), vp(xch.local.data_ptr()), world, r,
+                                                f_pay, f_flag, vp(f_cnt.data_ptr()), vp(f_cnt.data_ptr() + 4),
+                                                vp(xch.err.data_ptr()), B, C, HW, U.stream_ptr(DEV))
+            assert st == 0, U._lib.last_error()
+        for r, xch in enumerate(ranks):
+            (f_pay, f_flag, f_cnt), _ = slots[r]
+            out, sm, si = torch.empty_like(xs[r]), torch.empty(2 * C, device=DEV), torch.empty(2 * C + 1, device=DEV)
+            st = lib.pmt_bn_pair_apply_peer_f32(U.ptr(xs[r]), vp(xch.local.data_ptr()), world, f_pay, f_flag,
+                                                vp(f_cnt.data_ptr()), vp(xch.err.data_ptr()), U.ptr(weight), U.ptr(bias), None,
+                                                None, ctypes.c_float(mom), ctypes.c_float(eps), U.ptr(out), U.ptr(sm), U.ptr(si),
+                                                B, C, HW, 1, U.stream_ptr(DEV))
+            assert st == 0, U._lib.last_error()
+            got[r][:3] = [out, sm, si]
+        for r, xch in enumerate(ranks):
+            _, (b_pay, b_flag, b_cnt) = slots[r]
+            gw = torch.zeros(2, C, device=DEV)
+            st = lib.pmt_bn_pair_bwd_reduce_peer_f32(U.ptr(dys[r]), U.ptr(xs[r]), U.ptr(got[r][1]), U.ptr(got[r][2]),
+                                                     vp(xch.ptr_table.data_ptr()), vp(xch.local.data_ptr()), world, r, b_pay,
+                                                     b_flag, vp(b_cnt.data_ptr()), vp(b_cnt.data_ptr() + 4),
+                                                     vp(xch.err.data_ptr()), U.ptr(gw[0]), U.ptr(gw[1]), B, C, HW,
+                                                     U.ptr(weight), U.ptr(bias), 1, U.stream_ptr(DEV))
+            assert st == 0, U._lib.last_error()
+        for r, xch in enumerate(ranks):
+            _, (b_pay, b_flag, b_cnt) = slots[r]
+            dx = torch.empty_like(xs[r])
+            st = lib.pmt_bn_pair_bwd_apply_peer_f32(U.ptr(dys[r]), U.ptr(xs[r]), U.ptr(got[r][1]), U.ptr(got[r][2]),
+                                                    U.ptr(weight), vp(xch.local.data_ptr()), world, b_pay, b_flag,
+                                                    vp(b_cnt.data_ptr()), vp(xch.err.data_ptr()), U.ptr(dx), B, C, HW,
+                                                    U.ptr(bias), 1, U.stream_ptr(DEV))
+            assert st == 0, U._lib.last_error()
+            got[r][4] = dx
+        torch.cuda.synchronize()
+        for r in range(world):
+            for k in (0, 1, 2, 4):
+                assert torch.equal(got[r][k], want[r][k]), (step, r, k)
+            ranks[r].check()
+            assert int(slots[r][0][2][0]) == step + 1 and int(slots[r][1][2][0]) == step + 1   # epochs advanced on the device
