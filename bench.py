@@ -210,7 +210,7 @@ def run_step_record(world, timeout_s: float = 420.0):
                 "MASTER_PORT": str(int(os.environ.get("MASTER_PORT", "29511")) + 1)})
     for k in ("TORCHELASTIC_RUN_ID", "TORCHELASTIC_RESTART_COUNT", "TORCHELASTIC_MAX_RESTARTS", "GROUP_RANK", "ROLE_RANK"):
         env.pop(k, None)
-    cmd = [sys.executable, os.path.join(ROOT, "bench_step.py"), "--steps", "40", "--warmup", "5", "--json-out", out_path]
+    cmd = [sys.executable, os.path.join(ROOT, "bench_step.py"), "--steps", "30", "--warmup", "5", "--json-out", out_path]
     log = open(os.path.join(ROOT, "gpurun_out", f"step_n{world.world_size}_rank{world.rank}.log"), "w")
     t0 = time.time()
     try:

@@ -1,7 +1,10 @@
 #!/usr/bin/env python
-"""bench_step.py -- data-parallel training step (BASELINE configs 2 and 5): SDNetLite (DenseNet-121 siamese tower,
-1x17 correlation, decoders, disparity warp) fwd + loss + bwd + Adam on synthetic 256x512 stereo pairs, batch 4 per
-GPU, DDP + nn.SyncBatchNorm over NCCL/NVLink.  One process per GPU:
+"""bench_step.py -- data-parallel training step (BASELINE configs 2 and 5): SDNetLite (whole DenseNet-121 siamese tower --
+121 BatchNorm layers per pass --, 1x17 correlation + corrConv2d + ReLU, decoders, disparity warp + attention blend) fwd
++ CE/Lovasz/L1 loss + bwd + Adam on synthetic 256x512 stereo pairs, batch 4 per GPU, under DistributedDataParallel with
+synchronised batch norm.  NCCL carries the gradient all-reduce; the BN statistics travel over NVLink peer memory inside
+the bn_pair kernels (--nccl-bn: one NCCL collective per layer and direction instead).  One process per GPU; a single GPU
+runs the same code path in a 1-rank process group, so the N = 1 point of a scaling curve is the same configuration:
 
     python bench_step.py --steps 30                                        # 1 GPU (config 2)
     python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29533 \
@@ -38,13 +41,18 @@ def main():
     ap.add_argument("--nccl-bn", action="store_true", help="exchange the BN statistics with NCCL collectives (one all_gather / "
                                                            "all_reduce launch per layer and direction) instead of the "
                                                            "NVLink peer-memory exchange inside the bn_pair kernels")
-    ap.add_argument("--full-depth", action="store_true", help="whole DenseNet-121 per image (121 BN layers per tower pass)")
+    ap.add_argument("--shallow", action="store_true", help="stop the tower after denseblock2 (39 BN layers) instead of running "
+                                                           "the whole DenseNet-121 per image (121 BN layers per tower pass, the "
+                                                           "reference's `densenet` backbone)")
     ap.add_argument("--unfused", action="store_true", help="sampler -> conv -> relu and warp -> blend as separate ops")
     ap.add_argument("--no-lovasz", action="store_true", help="drop the Lovasz-Softmax term of the seg2 loss")
+    ap.add_argument("--plain-single", action="store_true", help="at 1 GPU run WITHOUT a process group (no DDP, stock BatchNorm); "
+                                                                "default: a 1-rank group, i.e. the N-GPU code path")
     ap.add_argument("--graph", action="store_true", help="(default) capture the whole step, NCCL collectives included, "
                                                          "in one CUDA graph")
     args = ap.parse_args()
-    if not args.eager and int(os.environ.get("WORLD_SIZE", "1")) > 1:
+    force_group = not args.plain_single
+    if not args.eager and (int(os.environ.get("WORLD_SIZE", "1")) > 1 or force_group):
         # capturing NCCL collectives: the watchdog must not query/abort work that lives inside a capture
         os.environ.setdefault("TORCH_NCCL_ASYNC_ERROR_HANDLING", "0")
         os.environ.setdefault("TORCH_NCCL_ENABLE_MONITORING", "0")
@@ -52,7 +60,8 @@ def main():
             import faulthandler
 
             faulthandler.dump_traceback_later(int(os.environ["PMT_STEP_HANG_DUMP"]), exit=True)
-    world = sharding.init_world("nccl" if int(os.environ.get("WORLD_SIZE", "1")) > 1 else None)
+    world = sharding.init_world("nccl" if (int(os.environ.get("WORLD_SIZE", "1")) > 1 or force_group) else None,
+                                force_group=force_group)
     dev = torch.device("cuda", world.local_rank)
     torch.cuda.set_device(dev)
     use_graph = not args.eager
@@ -60,7 +69,7 @@ def main():
     peer = paired and not args.nccl_bn and world.distributed
     step, model = harness.build_training_step(world, batch_per_gpu=args.batch, sync_bn=not args.no_sync_bn,
                                                cuda_graph=use_graph, paired_tower=not args.no_pair, peer_bn=peer,
-                                               full_depth=args.full_depth, fused_ops=not args.unfused,
+                                               full_depth=not args.shallow, fused_ops=not args.unfused,
                                                lovasz=not args.no_lovasz)
     for _ in range(max(args.warmup, 3)):
         loss = step()
@@ -84,7 +93,7 @@ def main():
                "ms_per_step": ms / args.steps, "scaling": "weak", "global_batch": args.batch * world.world_size,
                "params": n_params, "loss": float(loss.detach()), "sync_bn": not args.no_sync_bn,
                "cuda_graph": use_graph, "paired_tower": paired, "bn_exchange": "nvlink-peer" if peer else "nccl",
-               "full_depth": args.full_depth, "fused_ops": not args.unfused, "lovasz": not args.no_lovasz,
+               "full_depth": not args.shallow, "fused_ops": not args.unfused, "lovasz": not args.no_lovasz,
                "bn_layers_paired": n_bn_paired, "bn_layers_sync": n_bn_sync,
                "nccl_launches_per_step_bn": (0 if peer else 2 * n_bn_paired) + 2 * n_bn_sync if world.distributed else 0,
                "collectives": "DDP gradient all-reduce (NCCL); BN statistics: " +

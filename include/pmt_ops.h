@@ -199,8 +199,10 @@ int pmt_warp1d_mse_bwd_f32(const float* img, const float* off, const float* left
  *                updates running_mean/var (may be NULL) with momentum and the unbiased variance
  *   bwd_reduce : sums[(half*C+c)*2 + {0,1}] = sum dy, sum dy*(x-mean); gw/gb (C, ZEROED by the caller) += local grads
  *   bwd_apply  : sums after the cross-rank all-reduce; dx = (dy - sum_dy/N - (x-mean)*invstd^2*sum_dy_xmu/N)*invstd*weight
- * HW = H*W.  weight/bias may be NULL (non-affine).  relu != 0 fuses the ReLU that follows every BN of the reference's
- * towers (norm -> relu -> conv): apply clamps at 0, the backward kernels gate dy where the recomputed y was <= 0.
+ * HW = H*W.  weight/bias may be NULL (non-affine).  `relu` is a flag word: bit 0 fuses the ReLU that follows every BN of
+ * the reference's towers (norm -> relu -> conv): apply clamps at 0, the backward kernels gate dy where the recomputed y
+ * was <= 0; bit 1 ("merged") treats the two halves as ONE batch -- plain SyncBatchNorm statistics over the whole batch,
+ * one running-statistics update -- so the non-siamese layers of a model can use the same kernels and exchange.
  * ------------------------------------------------------------------------------------------- */
 int pmt_bn_pair_stats_f32(const float* x, float* payload, int B, int C, int HW, void* stream);
 int pmt_bn_pair_apply_f32(const float* x, const float* gathered, int world, const float* weight, const float* bias,
@@ -221,22 +223,26 @@ int pmt_bn_pair_bwd_apply_f32(const float* dy, const float* x, const float* save
  * offsets that are equal on all ranks, a payload region [2][world][n] (n = 4C+1 forward, 4C backward) and a flag
  * region [2][world] (int32, zero-initialised), plus LOCAL device words `epoch` (int, zero-initialised), `done`
  * (unsigned, zero-initialised) and a shared `err` word (set to 1 if a wait exceeded ~2 s).
- *   *_stats_peer / *_bwd_reduce_peer: compute, push the payload into slot [epoch parity][rank] of every peer, publish
- *       the new epoch to every peer's flag (st.release.sys) from the last block;
- *   *_apply_peer / *_bwd_apply_peer: wait (ld.acquire.sys) until all `world` flags show the local epoch, then read
- *       the payloads from local_buf (backward: summed in rank order -> bit-identical on all ranks).
+ *   *_stats_peer / *_bwd_reduce_peer: compute into this rank's slot [epoch parity][rank]; the last block copies the slot
+ *       into every peer's buffer, one thread fences at system scope, publishes the new epoch to every rank's flag
+ *       (st.release.sys) and -- wait_peers != 0 -- waits until all `world` flags of local_buf show that epoch
+ *       (wait_peers = 0 only when the ranks are emulated one after the other on ONE device: they must not wait for each
+ *       other inside a kernel);
+ *   *_apply_peer / *_bwd_apply_peer: read the payloads of all ranks from local_buf, no wait and no system-scope
+ *       operation (backward: summed in rank order -> bit-identical on all ranks).
  * Epochs advance on the device, so the sequence can be captured in a CUDA graph and replayed. */
 int pmt_bn_pair_stats_peer_f32(const float* x, void* const* peer_bufs, void* local_buf, int world, int rank,
-                               int64_t payload_off, int64_t flag_off, int* epoch, unsigned* done, int* err, int B, int C,
-                               int HW, void* stream);
+                               int64_t payload_off, int64_t flag_off, int* epoch, unsigned* done, int* err, int wait_peers,
+                               int B, int C, int HW, void* stream);
 int pmt_bn_pair_apply_peer_f32(const float* x, void* local_buf, int world, int64_t payload_off, int64_t flag_off,
                                int* epoch, int* err, const float* weight, const float* bias, float* running_mean,
                                float* running_var, float momentum, float eps, float* out, float* save_mean,
                                float* save_invstd, int B, int C, int HW, int relu, void* stream);
 int pmt_bn_pair_bwd_reduce_peer_f32(const float* dy, const float* x, const float* save_mean, const float* save_invstd,
                                     void* const* peer_bufs, void* local_buf, int world, int rank, int64_t payload_off,
-                                    int64_t flag_off, int* epoch, unsigned* done, int* err, float* gw, float* gb, int B,
-                                    int C, int HW, const float* weight, const float* bias, int relu, void* stream);
+                                    int64_t flag_off, int* epoch, unsigned* done, int* err, int wait_peers, float* gw,
+                                    float* gb, int B, int C, int HW, const float* weight, const float* bias, int relu,
+                                    void* stream);
 int pmt_bn_pair_bwd_apply_peer_f32(const float* dy, const float* x, const float* save_mean, const float* save_invstd,
                                    const float* weight, void* local_buf, int world, int64_t payload_off,
                                    int64_t flag_off, int* epoch, int* err, float* dx, int B, int C, int HW,

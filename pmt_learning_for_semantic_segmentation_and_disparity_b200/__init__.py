@@ -11,7 +11,7 @@ from .correlation import (CorrelationConvReLU, SpatialCorrelationSampler, Spatia
 from .psmnet import (build_concat_volume, disparityregression, matchshifted, softargmin,  # noqa: F401
                      upsample_softargmin)
 from .warp import apply_disparity, photo_consistency_mse, warp_blend  # noqa: F401
-from .syncbn import PairedSyncBatchNorm, PeerExchange, pair_batchnorms  # noqa: F401
+from .syncbn import PairedSyncBatchNorm, PeerExchange, pair_batchnorms, sync_batchnorms_to_peer  # noqa: F401
 from .compat import install_reference_shims  # noqa: F401
 
 __version__ = "0.1.0"

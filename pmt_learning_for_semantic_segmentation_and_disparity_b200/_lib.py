@@ -43,9 +43,9 @@ _SIGNATURES = {
     "pmt_bn_pair_apply_f32": [_P, _P, _I, _P, _P, _P, _P, _F, _F, _P, _P, _P, _I, _I, _I, _I, _P],
     "pmt_bn_pair_bwd_reduce_f32": [_P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _P, _P, _I, _P],
     "pmt_bn_pair_bwd_apply_f32": [_P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _P, _I, _P],
-    "pmt_bn_pair_stats_peer_f32": [_P, _P, _P, _I, _I, _L, _L, _P, _P, _P, _I, _I, _I, _P],
+    "pmt_bn_pair_stats_peer_f32": [_P, _P, _P, _I, _I, _L, _L, _P, _P, _P, _I, _I, _I, _I, _P],
     "pmt_bn_pair_apply_peer_f32": [_P, _P, _I, _L, _L, _P, _P, _P, _P, _P, _P, _F, _F, _P, _P, _P, _I, _I, _I, _I, _P],
-    "pmt_bn_pair_bwd_reduce_peer_f32": [_P, _P, _P, _P, _P, _P, _I, _I, _L, _L, _P, _P, _P, _P, _P, _I, _I, _I, _P, _P, _I, _P],
+    "pmt_bn_pair_bwd_reduce_peer_f32": [_P, _P, _P, _P, _P, _P, _I, _I, _L, _L, _P, _P, _P, _I, _P, _P, _I, _I, _I, _P, _P, _I, _P],
     "pmt_bn_pair_bwd_apply_peer_f32": [_P, _P, _P, _P, _P, _P, _I, _L, _L, _P, _P, _P, _I, _I, _I, _P, _I, _P],
     "pmt_warp1d_fwd_f32": [_P, _P, _P, _I, _I, _I, _I, _I, _P],
     "pmt_warp1d_bwd_f32": [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P],

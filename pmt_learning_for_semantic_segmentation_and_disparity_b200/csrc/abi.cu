@@ -49,12 +49,12 @@ int launch_bn_pair_bwd_reduce(const float*, const float*, const float*, const fl
 int launch_bn_pair_bwd_apply(const float*, const float*, const float*, const float*, const float*, const float*, float*, int,
                              int, int, const float*, int, cudaStream_t);
 int launch_bn_pair_stats_peer(const float*, void* const*, void*, int, int, long long, long long, int*, unsigned*, int*, int, int, int,
-                              cudaStream_t);
+                              int, cudaStream_t);
 int launch_bn_pair_apply_peer(const float*, void*, int, long long, long long, int*, int*, const float*, const float*, float*,
                               float*, float, float, float*, float*, float*, int, int, int, int, cudaStream_t);
 int launch_bn_pair_bwd_reduce_peer(const float*, const float*, const float*, const float*, void* const*, void*, int, int,
-                                   long long, long long, int*, unsigned*, int*, float*, float*, int, int, int, const float*,
-                                   const float*, int, cudaStream_t);
+                                   long long, long long, int*, unsigned*, int*, int, float*, float*, int, int, int,
+                                   const float*, const float*, int, cudaStream_t);
 int launch_bn_pair_bwd_apply_peer(const float*, const float*, const float*, const float*, const float*, void*, int, long long,
                                   long long, int*, int*, float*, int, int, int, const float*, int, cudaStream_t);
 int launch_warp_fwd(const float*, const float*, float*, int, int, int, int, int, cudaStream_t);
@@ -421,12 +421,12 @@ static int check_peer(const void* bufs_or_local, int world, int rank, int64_t pa
 }
 
 int pmt_bn_pair_stats_peer_f32(const float* x, void* const* peer_bufs, void* local_buf, int world, int rank,
-                               int64_t payload_off, int64_t flag_off, int* epoch, unsigned* done, int* err, int B, int C,
-                               int HW, void* stream) {
+                               int64_t payload_off, int64_t flag_off, int* epoch, unsigned* done, int* err, int wait_peers,
+                               int B, int C, int HW, void* stream) {
   PMT_CHECK_ARG(x && local_buf && done, "bn_pair: null pointer");
   PMT_CHECK_ARG(B >= 0 && C >= 0 && HW >= 0, "bn_pair: negative dimension");
   if (int e = check_peer(peer_bufs, world, rank, payload_off, flag_off, epoch, err)) return e;
-  return launch_bn_pair_stats_peer(x, peer_bufs, local_buf, world, rank, payload_off, flag_off, epoch, done, err, B, C, HW,
+  return launch_bn_pair_stats_peer(x, peer_bufs, local_buf, world, rank, payload_off, flag_off, epoch, done, err, wait_peers, B, C, HW,
                                    static_cast<cudaStream_t>(stream));
 }
 
@@ -445,13 +445,13 @@ int pmt_bn_pair_apply_peer_f32(const float* x, void* local_buf, int world, int64
 
 int pmt_bn_pair_bwd_reduce_peer_f32(const float* dy, const float* x, const float* save_mean, const float* save_invstd,
                                     void* const* peer_bufs, void* local_buf, int world, int rank, int64_t payload_off,
-                                    int64_t flag_off, int* epoch, unsigned* done, int* err, float* gw, float* gb, int B, int C,
-                                    int HW, const float* weight, const float* bias, int relu, void* stream) {
+                                    int64_t flag_off, int* epoch, unsigned* done, int* err, int wait_peers, float* gw, float* gb,
+                                    int B, int C, int HW, const float* weight, const float* bias, int relu, void* stream) {
   PMT_CHECK_ARG(dy && x && save_mean && save_invstd && gw && gb && local_buf && done, "bn_pair: null pointer");
   PMT_CHECK_ARG(B >= 0 && C >= 0 && HW >= 0, "bn_pair: negative dimension");
   if (int e = check_peer(peer_bufs, world, rank, payload_off, flag_off, epoch, err)) return e;
   return launch_bn_pair_bwd_reduce_peer(dy, x, save_mean, save_invstd, peer_bufs, local_buf, world, rank, payload_off, flag_off,
-                                        epoch, done, err, gw, gb, B, C, HW, weight, bias, relu,
+                                        epoch, done, err, wait_peers, gw, gb, B, C, HW, weight, bias, relu,
                                         static_cast<cudaStream_t>(stream));
 }
 

@@ -17,11 +17,12 @@
 // the payload themselves over NVLink peer memory, with NO collective launch on the dependency chain (a BN cannot
 // normalise before the statistics of all ranks are there, so the ~40 us an NCCL launch costs inside a CUDA graph is
 // paid once per layer and direction; it is what limited the 8-GPU training step to 5.7x):
-//   producer (stats / bwd_reduce): every block stores its (half, channel) pair straight into the symmetric buffer of
-//     EVERY rank (slot [parity][my rank]), __threadfence_system(), and counts itself on a local counter; the last block
-//     bumps the local epoch and writes it, st.release.sys, into the flag [parity][my rank] of every rank;
-//   consumer (apply / bwd_apply): every block spins (ld.acquire.sys) until the `world` flags of the current parity show
-//     the local epoch, then reads the payloads from its OWN copy of the buffer (peers pushed them) with ld.cg.
+//   producer (stats / bwd_reduce): every block stores its (half, channel) pair into this rank's OWN slot [parity][rank]
+//     and counts itself on a local counter; the last block copies the finished slot into the buffer of every peer, and
+//     one of its threads fences at system scope, writes the new epoch (st.release.sys) into the flag [parity][rank] of
+//     every rank and waits until the `world` flags of its own buffer show that epoch;
+//   consumer (apply / bwd_apply): reads the payloads of all ranks from its OWN copy of the buffer with ld.cg -- no wait,
+//     no system-scope operation (the producer kernel ahead of it in the stream has already waited).
 //   Slots are double-buffered by epoch parity, the epoch lives in device memory and advances inside the producer kernel,
 //   so a captured CUDA graph replays correctly.  A rank that waits longer than ~2 s sets *err and stops waiting (a hung
 //   peer must not hang this GPU).
@@ -46,47 +47,75 @@ struct PeerX {
   long long payload_off;  // float offset of this layer+direction's payload region [2 parity][world][n]
   long long flag_off;     // float offset of its flags [2 parity][world] (int32)
   int n;                  // payload floats per rank
-  int* epoch;             // local device counter of this layer+direction (starts at 0)
+  int* epoch;             // local device words of this layer+direction: [0] epoch (starts at 0), [2] epoch the local
+                          // consumers have already seen complete
   unsigned* done;         // local block counter (starts at 0; the last block resets it)
   int* err;               // set to 1 when a wait timed out
+  int wait;               // producer: 1 = wait for every rank's flag before the kernel ends (ranks on different GPUs);
+                          // 0 = publish only (ranks emulated one after the other on ONE GPU must not wait for each other)
 };
 
 __device__ __forceinline__ void st_release_sys(int* p, int v) {
   asm volatile("st.release.sys.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
-__device__ __forceinline__ int ld_acquire_sys(const int* p) {
+__device__ __forceinline__ int ld_relaxed_sys(const int* p) {
   int v;
-  asm volatile("ld.acquire.sys.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  asm volatile("ld.relaxed.sys.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
   return v;
 }
 
-// producer side, called by ONE thread per block after it has stored its payload values to every peer
+// Producer side, called by EVERY thread of every block after thread 0 has stored the block's payload values into this
+// rank's OWN slot (local memory, plain stores).  The last block of the grid copies the finished slot to every peer with
+// all its threads (one coalesced burst per peer); then ONE thread fences at system scope (cumulative over the block's
+// stores through the barrier), publishes the epoch to every rank's flag and waits until every rank's flag shows the same
+// epoch -- so the consumer kernel that follows in the stream finds all payloads in local memory and needs no wait and no
+// system-scope operation at all.  (Earlier versions let every producer block store + fence at system scope, and every
+// consumer block poll the flags: hundreds of system fences per layer made the exchange slower than the NCCL collective
+// it replaces, even on a single rank.)
 __device__ __forceinline__ void peer_publish(const PeerX& px, int e_next, unsigned n_blocks) {
-  __threadfence_system();                                   // this block's peer stores are visible system-wide
-  if (atomicAdd(px.done, 1u) == n_blocks - 1) {             // last block of the grid
+  __shared__ int s_last;
+  if (threadIdx.x == 0) {
+    __threadfence();                                        // this block's slot values are visible device-wide
+    s_last = atomicAdd(px.done, 1u) == n_blocks - 1 ? 1 : 0;
+  }
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  const int par = e_next & 1;
+  const long long slot = px.payload_off + ((long long)par * px.world + px.rank) * px.n;
+  const float* src = px.local + slot;
+  for (int r = 0; r < px.world; ++r) {
+    if (r == px.rank) continue;
+    float* dst = px.bufs[r] + slot;
+    for (int i = threadIdx.x; i < px.n; i += blockDim.x) dst[i] = __ldcg(src + i);
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
     *px.done = 0u;
     *px.epoch = e_next;                                     // read by the consumer kernel that follows in the stream
-    __threadfence_system();
-    const int par = e_next & 1;
-    for (int r = 0; r < px.world; ++r)
-      st_release_sys(reinterpret_cast<int*>(px.bufs[r] + px.flag_off) + par * px.world + px.rank, e_next);
+    if (px.world > 1) {
+      __threadfence_system();                               // the remote copies are visible before the flags
+      for (int r = 0; r < px.world; ++r)
+        st_release_sys(reinterpret_cast<int*>(px.bufs[r] + px.flag_off) + par * px.world + px.rank, e_next);
+      const int* flags = reinterpret_cast<const int*>(px.local + px.flag_off) + par * px.world;
+      const long long t0 = clock64();
+      for (int r = 0; r < px.world && px.wait; ++r) {
+        while (ld_relaxed_sys(flags + r) != e_next) {
+          if (clock64() - t0 > (1ll << 32)) {               // ~2 s: give up instead of hanging the GPU
+            *px.err = 1;
+            break;
+          }
+        }
+      }
+      asm volatile("fence.acq_rel.sys;" ::: "memory");       // the payloads behind the flags are visible
+    }
   }
 }
 
-// consumer side: returns the base of the [world][n] payloads of the current epoch once every rank has published
+// Consumer side: the base of the [world][n] payloads of the current epoch (complete: the producer kernel waited)
 __device__ __forceinline__ const float* peer_wait(const PeerX& px) {
-  const int e = *px.epoch, par = e & 1;
-  const int* flags = reinterpret_cast<const int*>(px.local + px.flag_off) + par * px.world;
-  const long long t0 = clock64();
-  for (int r = 0; r < px.world; ++r) {
-    while (ld_acquire_sys(flags + r) != e) {
-      if (clock64() - t0 > (1ll << 32)) {                   // ~2 s: give up instead of hanging the GPU
-        *px.err = 1;
-        break;
-      }
-    }
-  }
-  return px.local + px.payload_off + (long long)par * px.world * px.n;
+  const int e = *px.epoch;
+  return px.local + px.payload_off + (long long)(e & 1) * px.world * px.n;
 }
 
 // block-wide sum of two values; result valid in every thread
@@ -143,34 +172,37 @@ __global__ void __launch_bounds__(kBnThreads) bn_pair_stats_kernel(const float* 
       if (c == 0 && half == 0) payload[4 * C] = n;   // this rank's element count per channel-half
     } else {
       const int e_next = *px.epoch + 1;              // every block reads the same value: only the last block advances it
-      const long long slot = px.payload_off + ((long long)(e_next & 1) * px.world + px.rank) * px.n;
-      for (int r = 0; r < px.world; ++r) {
-        float* dst = px.bufs[r] + slot;
-        dst[(half * C + c) * 2 + 0] = mean;
-        dst[(half * C + c) * 2 + 1] = m2;
-        if (c == 0 && half == 0) dst[4 * C] = n;
-      }
-      peer_publish(px, e_next, gridDim.x * gridDim.y);
+      float* dst = px.local + px.payload_off + ((long long)(e_next & 1) * px.world + px.rank) * px.n;   // own slot
+      dst[(half * C + c) * 2 + 0] = mean;
+      dst[(half * C + c) * 2 + 1] = m2;
+      if (c == 0 && half == 0) dst[4 * C] = n;
     }
   }
+  if (px.bufs != nullptr) peer_publish(px, *px.epoch + 1, gridDim.x * gridDim.y);
 }
 
 // Chan et al.: combine (n_r, mean_r, M2_r) of `world` ranks.  gathered = [world][4C+1]: [half][c][2] then the count.
+// merged: the two halves are ONE batch (plain SyncBatchNorm semantics): every (rank, half) is a group of its own.
 __device__ __forceinline__ void combine(const float* __restrict__ gathered, int world, int stride, int half, int c, int C,
-                                        float& mean, float& var_biased, float& n_total) {
+                                        float& mean, float& var_biased, float& n_total, int merged = 0) {
   // ld.cg: with the peer exchange the payloads were written by other GPUs (never read them through L1)
+  const int h0 = merged ? 0 : half, h1 = merged ? 1 : half;
   float N = 0.f, m = 0.f;
   for (int r = 0; r < world; ++r) {
     const float n = __ldcg(gathered + r * stride + 4 * C);
-    N += n;
-    m = fmaf(n, __ldcg(gathered + r * stride + (half * C + c) * 2), m);
+    for (int hh = h0; hh <= h1; ++hh) {
+      N += n;
+      m = fmaf(n, __ldcg(gathered + r * stride + (hh * C + c) * 2), m);
+    }
   }
   m /= N;
   float M2 = 0.f;
   for (int r = 0; r < world; ++r) {
     const float n = __ldcg(gathered + r * stride + 4 * C);
-    const float d = __ldcg(gathered + r * stride + (half * C + c) * 2) - m;
-    M2 += __ldcg(gathered + r * stride + (half * C + c) * 2 + 1) + n * d * d;
+    for (int hh = h0; hh <= h1; ++hh) {
+      const float d = __ldcg(gathered + r * stride + (hh * C + c) * 2) - m;
+      M2 += __ldcg(gathered + r * stride + (hh * C + c) * 2 + 1) + n * d * d;
+    }
   }
   mean = m, var_biased = M2 / N, n_total = N;
 }
@@ -188,8 +220,9 @@ __global__ void __launch_bounds__(kBnThreads) bn_pair_apply_kernel(const float* 
   __shared__ float s_scale, s_shift;
   if (threadIdx.x == 0) {
     if (px.bufs != nullptr) gathered = peer_wait(px);   // every rank's payload has landed in this rank's buffer
+    const int merged = (relu >> 1) & 1;                   // flags: bit 0 = fused ReLU, bit 1 = the halves are one batch
     float mean, var, N;
-    combine(gathered, world, stride, half, c, C, mean, var, N);
+    combine(gathered, world, stride, half, c, C, mean, var, N, merged);
     const float invstd = rsqrtf(var + eps);
     const float w = weight ? weight[c] : 1.f, bb = bias ? bias[c] : 0.f;
     s_scale = invstd * w;
@@ -204,16 +237,18 @@ __global__ void __launch_bounds__(kBnThreads) bn_pair_apply_kernel(const float* 
       float rm = running_mean[c], rv = running_var[c];
       rm = (1.f - momentum) * rm + momentum * mean;
       rv = (1.f - momentum) * rv + momentum * var * (N / fmaxf(N - 1.f, 1.f));
-      float mean2, var2, N2;
-      combine(gathered, world, stride, 1, c, C, mean2, var2, N2);
-      rm = (1.f - momentum) * rm + momentum * mean2;
-      rv = (1.f - momentum) * rv + momentum * var2 * (N2 / fmaxf(N2 - 1.f, 1.f));
+      if (!merged) {   // two calls of one BatchNorm: the right half updates after the left one
+        float mean2, var2, N2;
+        combine(gathered, world, stride, 1, c, C, mean2, var2, N2);
+        rm = (1.f - momentum) * rm + momentum * mean2;
+        rv = (1.f - momentum) * rv + momentum * var2 * (N2 / fmaxf(N2 - 1.f, 1.f));
+      }
       running_mean[c] = rm, running_var[c] = rv;
     }
   }
   __syncthreads();
   const float sc = s_scale, sh = s_shift;
-  const float lo = relu ? 0.f : -INFINITY;   // fused ReLU: y = max(bn(x), 0)
+  const float lo = (relu & 1) ? 0.f : -INFINITY;   // fused ReLU: y = max(bn(x), 0)
   const float* xr = x + (int64_t)row * HW;
   float* o = out + (int64_t)row * HW;
   if ((HW & 3) == 0) {
@@ -242,7 +277,7 @@ __global__ void __launch_bounds__(kBnThreads) bn_pair_bwd_reduce_kernel(const fl
   // fused ReLU: the incoming gradient only counts where y = (x-mean)*invstd*w + b was positive (y recomputed from x)
   const float ysc = save_invstd[half * C + c] * (weight ? weight[c] : 1.f);
   const float ysh = (bias ? bias[c] : 0.f) - mean * ysc;
-  auto gate = [&](float g, float v) { return (!relu || fmaf(v, ysc, ysh) > 0.f) ? g : 0.f; };
+  auto gate = [&](float g, float v) { return (!(relu & 1) || fmaf(v, ysc, ysh) > 0.f) ? g : 0.f; };
   float s1 = 0.f, s2 = 0.f;
   const bool vec = (HW & 3) == 0;
   for (int b = 0; b < B; ++b) {
@@ -275,15 +310,12 @@ __global__ void __launch_bounds__(kBnThreads) bn_pair_bwd_reduce_kernel(const fl
       sums[(half * C + c) * 2 + 1] = s2;
     } else {
       const int e_next = *px.epoch + 1;
-      const long long slot = px.payload_off + ((long long)(e_next & 1) * px.world + px.rank) * px.n;
-      for (int r = 0; r < px.world; ++r) {
-        float* dst = px.bufs[r] + slot;
-        dst[(half * C + c) * 2 + 0] = s1;
-        dst[(half * C + c) * 2 + 1] = s2;
-      }
-      peer_publish(px, e_next, gridDim.x * gridDim.y);
+      float* dst = px.local + px.payload_off + ((long long)(e_next & 1) * px.world + px.rank) * px.n;   // own slot
+      dst[(half * C + c) * 2 + 0] = s1;
+      dst[(half * C + c) * 2 + 1] = s2;
     }
   }
+  if (px.bufs != nullptr) peer_publish(px, *px.epoch + 1, gridDim.x * gridDim.y);
 }
 
 // grid (2B*C).  sums are the all-reduced [2][C][2]; save_invstd[2C] = elements per channel-half over all ranks.
@@ -298,14 +330,22 @@ __global__ void __launch_bounds__(kBnThreads) bn_pair_bwd_apply_kernel(const flo
   const int row = blockIdx.x, b = row / C, c = row % C, half = b >= B ? 1 : 0;
   const float mean = save_mean[half * C + c], invstd = save_invstd[half * C + c];
   __shared__ float s_sum[2];
-  if (px.bufs != nullptr) {
-    // all-reduce in place of NCCL: wait for every rank's sums, add them in rank order (identical on all ranks)
+  const int merged = (relu >> 1) & 1;
+  if (px.bufs != nullptr || merged) {
+    // all-reduce in place of NCCL: wait for every rank's sums, add them in rank order (identical on all ranks);
+    // merged: both halves belong to one batch, their sums add up
     if (threadIdx.x == 0) {
-      const float* all = peer_wait(px);
+      const int h0 = merged ? 0 : half, h1 = merged ? 1 : half;
       float a0 = 0.f, a1 = 0.f;
-      for (int r = 0; r < px.world; ++r) {
-        a0 += __ldcg(all + (long long)r * px.n + (half * C + c) * 2);
-        a1 += __ldcg(all + (long long)r * px.n + (half * C + c) * 2 + 1);
+      if (px.bufs != nullptr) {
+        const float* all = peer_wait(px);
+        for (int r = 0; r < px.world; ++r)
+          for (int hh = h0; hh <= h1; ++hh) {
+            a0 += __ldcg(all + (long long)r * px.n + (hh * C + c) * 2);
+            a1 += __ldcg(all + (long long)r * px.n + (hh * C + c) * 2 + 1);
+          }
+      } else {
+        for (int hh = h0; hh <= h1; ++hh) a0 += sums[(hh * C + c) * 2], a1 += sums[(hh * C + c) * 2 + 1];
       }
       s_sum[0] = a0, s_sum[1] = a1;
     }
@@ -313,10 +353,11 @@ __global__ void __launch_bounds__(kBnThreads) bn_pair_bwd_apply_kernel(const flo
   }
   const float w = weight ? weight[c] : 1.f;
   const float ysc = invstd * w, ysh = (bias ? bias[c] : 0.f) - mean * ysc;
-  auto gate = [&](float g, float v) { return (!relu || fmaf(v, ysc, ysh) > 0.f) ? g : 0.f; };
+  auto gate = [&](float g, float v) { return (!(relu & 1) || fmaf(v, ysc, ysh) > 0.f) ? g : 0.f; };
   const float n_total = save_invstd[2 * C];
-  const float mean_dy = (px.bufs != nullptr ? s_sum[0] : sums[(half * C + c) * 2]) / n_total;
-  const float k = (px.bufs != nullptr ? s_sum[1] : sums[(half * C + c) * 2 + 1]) / n_total * invstd * invstd;
+  const bool from_smem = px.bufs != nullptr || merged;
+  const float mean_dy = (from_smem ? s_sum[0] : sums[(half * C + c) * 2]) / n_total;
+  const float k = (from_smem ? s_sum[1] : sums[(half * C + c) * 2 + 1]) / n_total * invstd * invstd;
   const float sc = invstd * w;
   const float* g = dy + (int64_t)row * HW;
   const float* xr = x + (int64_t)row * HW;
@@ -342,11 +383,11 @@ __global__ void __launch_bounds__(kBnThreads) bn_pair_bwd_apply_kernel(const flo
 
 namespace {
 PeerX make_px(void* const* bufs, void* local, int world, int rank, long long payload_off, long long flag_off, int n, int* epoch,
-              unsigned* done, int* err) {
+              unsigned* done, int* err, int wait = 0) {
   PeerX px{};
   px.bufs = reinterpret_cast<float* const*>(bufs), px.local = static_cast<float*>(local);
   px.world = world, px.rank = rank, px.payload_off = payload_off, px.flag_off = flag_off, px.n = n;
-  px.epoch = epoch, px.done = done, px.err = err;
+  px.epoch = epoch, px.done = done, px.err = err, px.wait = wait;
   return px;
 }
 }  // namespace
@@ -391,10 +432,11 @@ int launch_bn_pair_bwd_apply(const float* dy, const float* x, const float* save_
 
 // ---- the same four steps with the NVLink peer exchange instead of a collective between them ----
 int launch_bn_pair_stats_peer(const float* x, void* const* bufs, void* local, int world, int rank, long long payload_off,
-                              long long flag_off, int* epoch, unsigned* done, int* err, int B, int C, int HW, cudaStream_t st) {
+                              long long flag_off, int* epoch, unsigned* done, int* err, int wait, int B, int C, int HW,
+                              cudaStream_t st) {
   if (B == 0 || C == 0 || HW == 0) return PMT_OK;
   bn_pair_stats_kernel<<<dim3((unsigned)C, 2), kBnThreads, 0, st>>>(
-      x, nullptr, B, C, HW, make_px(bufs, local, world, rank, payload_off, flag_off, 4 * C + 1, epoch, done, err));
+      x, nullptr, B, C, HW, make_px(bufs, local, world, rank, payload_off, flag_off, 4 * C + 1, epoch, done, err, wait));
   PMT_LAUNCH_OK("bn_pair_stats_kernel<peer>");
   return PMT_OK;
 }
@@ -414,12 +456,12 @@ int launch_bn_pair_apply_peer(const float* x, void* local, int world, long long 
 
 int launch_bn_pair_bwd_reduce_peer(const float* dy, const float* x, const float* save_mean, const float* save_invstd,
                                    void* const* bufs, void* local, int world, int rank, long long payload_off,
-                                   long long flag_off, int* epoch, unsigned* done, int* err, float* gw, float* gb, int B, int C,
-                                   int HW, const float* weight, const float* bias, int relu, cudaStream_t st) {
+                                   long long flag_off, int* epoch, unsigned* done, int* err, int wait, float* gw, float* gb,
+                                   int B, int C, int HW, const float* weight, const float* bias, int relu, cudaStream_t st) {
   if (B == 0 || C == 0 || HW == 0) return PMT_OK;
   bn_pair_bwd_reduce_kernel<<<dim3((unsigned)C, 2), kBnThreads, 0, st>>>(
       dy, x, save_mean, save_invstd, nullptr, gw, gb, B, C, HW, weight, bias, relu,
-      make_px(bufs, local, world, rank, payload_off, flag_off, 4 * C, epoch, done, err));
+      make_px(bufs, local, world, rank, payload_off, flag_off, 4 * C, epoch, done, err, wait));
   PMT_LAUNCH_OK("bn_pair_bwd_reduce_kernel<peer>");
   return PMT_OK;
 }

@@ -301,9 +301,12 @@ corr1d_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmL, const __grid_const
 // it with tcgen05.st as hi (raw fp32: kind::tf32 ignores the low 13 mantissa bits) and lo = x - trunc_tf32(x) into a
 // 4-slot A ring in TMEM columns [384, 512), and the MMAs take A from TMEM (TS form).  Per 128 x 192 tile that removes
 // 192 KB of operand fetches and the L share of the lo ring (32 KB read + 32 KB written) from shared memory.
-//   warp 0 TMA producer | warp 1 MMA issuer | warps 2-5 epilogue | warps 6-9 A builders | warps 10-13 R lo split (3xTF32)
+//   warp 0 TMA producer | warp 1 MMA issuer | warps 2-9 epilogue (two per TMEM lane quarter, each takes one half of
+//   every 32-column block: the drain, serialised with the MMA phase on the single 320-column accumulator, was the longest
+//   part of a tile with four warps) | warps 10-13 A builders | warps 14-15 R lo split (3xTF32)
 // --------------------------------------------------------------------------------------------------------------------
-constexpr int kTcaThreads3 = 32 * 14, kTcaThreads1 = 32 * 10;
+constexpr int kTcaEpiWarps = 8;
+constexpr int kTcaThreads3 = 32 * 16, kTcaThreads1 = 32 * 14;   // 16 warps: 128 registers per thread
 
 template <int kPasses>
 __global__ void __launch_bounds__(kPasses == 3 ? kTcaThreads3 : kTcaThreads1, 1)
@@ -328,7 +331,7 @@ corr1d_fwd_tca_kernel(const __grid_constant__ CUtensorMap tmL, const __grid_cons
     for (int s = 0; s < 8; ++s) {
       mbar_init(&full[s], 1);
       mbar_init(&empty[s], 1);
-      mbar_init(&xf_done[s], 4);
+      mbar_init(&xf_done[s], 2);
       mbar_init(&lo_empty[s], 1);
       mbar_init(&l_full[s], 1);
       mbar_init(&l_empty[s], 4);
@@ -338,7 +341,7 @@ corr1d_fwd_tca_kernel(const __grid_constant__ CUtensorMap tmL, const __grid_cons
       mbar_init(&a_empty[s], 1);
     }
     mbar_init(tmem_full, 1);
-    mbar_init(tmem_empty, 4);
+    mbar_init(tmem_empty, kTcaEpiWarps);
     fence_mbar_init();
   }
   if (wid == 1) {
@@ -434,21 +437,27 @@ corr1d_fwd_tca_kernel(const __grid_constant__ CUtensorMap tmL, const __grid_cons
         }
       }
     }
-  } else if (wid < 6) {
-    // ===== epilogue warps: TMEM -> registers -> un-skewed staging tile -> TMA store (as in the SS kernel) =====
+  } else if (wid < 2 + kTcaEpiWarps) {
+    // ===== epilogue warps: TMEM -> registers -> un-skewed staging tile -> TMA store =====
+    // Block b (32 TMEM columns from column delta + 32 b) holds for lane w = 32q+lane the planes 32(b-q) + jj - lane, so
+    // the planes [32s, 32s+32) of this warp's 32 output columns are the upper triangle (jj >= lane) of block s+q and the
+    // lower triangle of block s+q+1: every block is read from TMEM once and kept for the next step.  Two warps share a
+    // lane quarter: warp `hsel` owns columns jj in [16 hsel, 16 hsel + 16) of every block.
     const int q = wid & 3;               // TMEM lane quarter this warp may access
+    const int hsel = (wid - 2) >> 2;     // which half of every block
     const int wl = 32 * q + lane;        // output column within the tile (= TMEM lane)
     int it = 0, gstep = 0;
     for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x, ++it) {
       const int wt = tile % a.n_wtiles, h = (tile / a.n_wtiles) % a.H, n = tile / (a.n_wtiles * a.H);
       mbar_wait(tmem_full, (uint32_t)it & 1u);
       tc::fence_after_sync();
-      float vp[32], vc[32];
-      tc::tmem_ld32(tmem_base + ((uint32_t)(32 * q) << 16) + (uint32_t)(32 * q + a.delta), vp);
-      const int r0 = (32 - lane) & 31;
+      float vp[16], vc[16];
+      const uint32_t tcol = tmem_base + ((uint32_t)(32 * q) << 16) + (uint32_t)(a.delta + 16 * hsel);
+      tc::tmem_ld16(tcol + (uint32_t)(32 * q), vp);
+      const int r0 = (32 - lane + 16 * hsel) & 31;
       for (int s = 0; s < a.n_steps; ++s, ++gstep) {
         float* tile_s = reinterpret_cast<float*>(smem + a.tile_off + (gstep % a.n_bufs) * kStepBytes);
-        tc::tmem_ld32(tmem_base + ((uint32_t)(32 * q) << 16) + (uint32_t)(32 * (s + q + 1) + a.delta), vc);
+        tc::tmem_ld16(tcol + (uint32_t)(32 * (s + q + 1)), vc);
         if (s == a.n_steps - 1) {
           tc::fence_before_sync();
           __syncwarp();
@@ -458,17 +467,18 @@ corr1d_fwd_tca_kernel(const __grid_constant__ CUtensorMap tmL, const __grid_cons
           if (a.n_bufs == 3) tc::tma_store_wait_read<2>();
           else tc::tma_store_wait_read<1>();
         }
-        named_bar_sync(1, 128);
+        named_bar_sync(1, 32 * kTcaEpiWarps);
         float* col = tile_s + wl;
 #pragma unroll
-        for (int jj = 0; jj < 32; ++jj) {
-          const float v = (jj >= lane) ? vp[jj] : vc[jj];
-          col[((r0 + jj) & 31) * kTM] = v;       // staging row = plane - 32s = (jj - lane) mod 32
+        for (int j = 0; j < 16; ++j) {
+          const int jj = 16 * hsel + j;
+          const float v = (jj >= lane) ? vp[j] : vc[j];
+          col[((r0 + j) & 31) * kTM] = v;        // staging row = plane - 32s = (jj - lane) mod 32
         }
 #pragma unroll
-        for (int jj = 0; jj < 32; ++jj) vp[jj] = vc[jj];
+        for (int j = 0; j < 16; ++j) vp[j] = vc[j];
         fence_proxy_async();                       // generic-proxy writes -> visible to the TMA store
-        named_bar_sync(1, 128);
+        named_bar_sync(1, 32 * kTcaEpiWarps);
         if (wid == 2 && lane == 0) {
           tc::tma_store_4d(&tmO, tile_s, wt * kTM, h, kRowsPerStep * s, n);
           tc::tma_store_commit();
@@ -476,7 +486,7 @@ corr1d_fwd_tca_kernel(const __grid_constant__ CUtensorMap tmL, const __grid_cons
       }
     }
     if (wid == 2 && lane == 0) tc::tma_store_wait<0>();
-  } else if (wid < 10) {
+  } else if (wid < 2 + kTcaEpiWarps + 4) {
     // ===== A builders: L slab (shared memory, [16 ch][128 w]) -> TMEM A slot, hi = raw fp32, lo = x - trunc_tf32(x) =====
     const int q = wid & 3;
     const int xl = 32 * q + lane;        // output column = TMEM lane = A row
@@ -511,7 +521,8 @@ corr1d_fwd_tca_kernel(const __grid_constant__ CUtensorMap tmL, const __grid_cons
     }
   } else {
     // ===== R lo split (kPasses == 3): lo = x - trunc_tf32(x) of the landed band stage into the lo ring =====
-    const int t = tid - 10 * 32;             // 0..127
+    constexpr int kXfThreads = 64;
+    const int t = tid - 32 * (2 + kTcaEpiWarps + 4);   // 0..63
     const int nchunks = a.NB * (kBoxBytes / 16);
     int st = 0, ls = 0;
     uint32_t fph = 0, leph = 1;
@@ -521,20 +532,20 @@ corr1d_fwd_tca_kernel(const __grid_constant__ CUtensorMap tmL, const __grid_cons
         mbar_wait(&lo_empty[ls], leph);
         const unsigned char* sbase = smem + (size_t)st * a.stage_bytes;
         unsigned char* lbase = smem + a.lo_ring_off + (size_t)ls * a.stage_bytes;
-        for (int cb = t; cb < nchunks; cb += 8 * 128) {
+        for (int cb = t; cb < nchunks; cb += 8 * kXfThreads) {
           float4 x[8];
 #pragma unroll
           for (int u = 0; u < 8; ++u)
-            if (cb + u * 128 < nchunks) x[u] = *reinterpret_cast<const float4*>(sbase + 16 * (cb + u * 128));
+            if (cb + u * kXfThreads < nchunks) x[u] = *reinterpret_cast<const float4*>(sbase + 16 * (cb + u * kXfThreads));
 #pragma unroll
           for (int u = 0; u < 8; ++u) {
-            if (cb + u * 128 < nchunks) {
+            if (cb + u * kXfThreads < nchunks) {
               float4 lo;
               lo.x = x[u].x - __uint_as_float(__float_as_uint(x[u].x) & 0xffffe000u);
               lo.y = x[u].y - __uint_as_float(__float_as_uint(x[u].y) & 0xffffe000u);
               lo.z = x[u].z - __uint_as_float(__float_as_uint(x[u].z) & 0xffffe000u);
               lo.w = x[u].w - __uint_as_float(__float_as_uint(x[u].w) & 0xffffe000u);
-              *reinterpret_cast<float4*>(lbase + 16 * (cb + u * 128)) = lo;
+              *reinterpret_cast<float4*>(lbase + 16 * (cb + u * kXfThreads)) = lo;
             }
           }
         }

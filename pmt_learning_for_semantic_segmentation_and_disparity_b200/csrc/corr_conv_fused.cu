@@ -22,7 +22,16 @@ namespace {
 
 constexpr int kFThreads = 256;
 constexpr int kFChunk = 32;     // channels per shared-memory stage
+constexpr int kFStages = 4;     // max cp.async ring depth: three chunks in flight while one is consumed (with two stages the row
+                                // loop ran at one global-memory latency per chunk: 20 us for 11 chunks)
 constexpr int kFMaxW = 128;
+
+__device__ __forceinline__ void cp_async_wait_dyn(int pending) {   // pending = groups allowed to stay in flight
+  if (pending >= 3) cp_async_wait<3>();
+  else if (pending == 2) cp_async_wait<2>();
+  else if (pending == 1) cp_async_wait<1>();
+  else cp_async_wait<0>();
+}
 
 struct FusedArgs {
   const float* a;      // in1 (B,C,H,W)
@@ -39,6 +48,7 @@ struct FusedArgs {
   int Wp;              // W + 2*pad
   int G;               // channel groups per chunk = kFThreads / (W/2), rounded down (threads beyond G*W/2 idle in the filters)
   float scale;         // 1 (1-D patch: not divided by C)
+  int stages;          // cp.async ring depth (2..kFStages), as many as shared memory allows
 };
 
 // stage one 32-channel chunk of rows a[n,c0..,h,:] and b[...] into [kFChunk][Wp] tiles (interior at column pad)
@@ -54,24 +64,23 @@ __device__ __forceinline__ void stage_chunk(const FusedArgs& f, float* As, float
     float* dst = (second ? Bs : As) + c * f.Wp + f.pad + 4 * q;
     cp_async16(dst, src, valid);
   }
-  cp_async_commit();
 }
 
 template <int kP>
 __global__ void __launch_bounds__(kFThreads) corr_conv_relu_fwd_kernel(const FusedArgs f) {
   extern __shared__ __align__(16) float sm[];
   constexpr int r = (kP - 1) / 2;
-  const int W = f.W, Wp = f.Wp, pairs = W / 2, G = f.G;
-  float* As = sm;                                  // [2][kFChunk][Wp]
-  float* Bs = As + 2 * kFChunk * Wp;               // [2][kFChunk][Wp]
-  float* part = Bs + 2 * kFChunk * Wp;             // [G][kP][W]
+  const int W = f.W, Wp = f.Wp, pairs = W / 2, G = f.G, S = f.stages;
+  float* As = sm;                                  // [S][kFChunk][Wp]
+  float* Bs = As + S * kFChunk * Wp;               // [S][kFChunk][Wp]
+  float* part = Bs + S * kFChunk * Wp;             // [G][kP][W]
   float* cs = part + G * kP * W;                   // [kP][W]
   float* ws = cs + kP * W;                         // [O][kP]
   const int tid = threadIdx.x;
   const int pair = tid % pairs, grp = tid / pairs;
   const bool worker = grp < G;
   const int n_chunks = (f.C + kFChunk - 1) / kFChunk;
-  for (int i = tid; i < 4 * kFChunk * Wp; i += kFThreads) As[i] = 0.f;   // zero halos (never overwritten)
+  for (int i = tid; i < 2 * S * kFChunk * Wp; i += kFThreads) As[i] = 0.f;   // zero halos (never overwritten)
   for (int i = tid; i < f.O * kP; i += kFThreads) ws[i] = __ldg(f.wt + i);
   __syncthreads();
   for (int row = blockIdx.x; row < f.B * f.H; row += gridDim.x) {
@@ -79,14 +88,17 @@ __global__ void __launch_bounds__(kFThreads) corr_conv_relu_fwd_kernel(const Fus
     float acc0[kP], acc1[kP];
 #pragma unroll
     for (int p = 0; p < kP; ++p) acc0[p] = 0.f, acc1[p] = 0.f;
-    stage_chunk(f, As, Bs, n, h, 0, tid);
+    for (int k = 0; k < S - 1; ++k) {               // prologue: S-1 chunks in flight (one commit group each)
+      if (k < n_chunks) stage_chunk(f, As + k * kFChunk * Wp, Bs + k * kFChunk * Wp, n, h, k * kFChunk, tid);
+      cp_async_commit();
+    }
     for (int k = 0; k < n_chunks; ++k) {
-      const int s = k & 1;
-      if (k + 1 < n_chunks) {
-        stage_chunk(f, As + (s ^ 1) * kFChunk * Wp, Bs + (s ^ 1) * kFChunk * Wp, n, h, (k + 1) * kFChunk, tid);
-        cp_async_wait<1>();
-      } else {
-        cp_async_wait<0>();
+      const int s = k % S;
+      {
+        const int kn = k + S - 1, sn = kn % S;      // refill the stage consumed in the previous iteration
+        if (kn < n_chunks) stage_chunk(f, As + sn * kFChunk * Wp, Bs + sn * kFChunk * Wp, n, h, kn * kFChunk, tid);
+        cp_async_commit();
+        cp_async_wait_dyn(S - 1);                   // chunk k has landed
       }
       __syncthreads();
       if (worker) {
@@ -150,10 +162,10 @@ __global__ void __launch_bounds__(kFThreads) corr_conv_relu_bwd_kernel(const Fus
   extern __shared__ __align__(16) float sm[];
   constexpr int r = (kP - 1) / 2;
   constexpr int kPq = (kP + 3) & ~3;               // padded P for float4 rows
-  const int W = f.W, Wp = f.Wp, pairs = W / 2, G = f.G, O = f.O;
-  float* As = sm;                                  // [2][kFChunk][Wp]
-  float* Bs = As + 2 * kFChunk * Wp;               // [2][kFChunk][Wp]
-  float* gzm = Bs + 2 * kFChunk * Wp;              // [O][W+1]   masked upstream gradient
+  const int W = f.W, Wp = f.Wp, pairs = W / 2, G = f.G, O = f.O, S = f.stages;
+  float* As = sm;                                  // [S][kFChunk][Wp]
+  float* Bs = As + S * kFChunk * Wp;               // [S][kFChunk][Wp]
+  float* gzm = Bs + S * kFChunk * Wp;              // [O][W+1]   masked upstream gradient
   float* ct = gzm + O * (W + 1);                   // [W][kPq]   saved slab, transposed
   float* ws = ct + W * kPq;                        // [O][kPq]
   float* gc = ws + O * kPq;                        // [kP][W]    gradient of the slab
@@ -163,12 +175,15 @@ __global__ void __launch_bounds__(kFThreads) corr_conv_relu_bwd_kernel(const Fus
   const bool worker = grp < G;
   const int n_chunks = (f.C + kFChunk - 1) / kFChunk;
   const int n_og = kFThreads / W > 0 ? kFThreads / W : 1;
-  for (int i = tid; i < 4 * kFChunk * Wp; i += kFThreads) As[i] = 0.f;   // zero halos
+  for (int i = tid; i < 2 * S * kFChunk * Wp; i += kFThreads) As[i] = 0.f;   // zero halos
   for (int i = tid; i < O * kPq; i += kFThreads) ws[i] = (i % kPq) < kP ? __ldg(f.wt + (i / kPq) * kP + i % kPq) : 0.f;
   __syncthreads();
   for (int row = blockIdx.x; row < f.B * f.H; row += gridDim.x) {
     const int n = row / f.H, h = row % f.H;
-    stage_chunk(f, As, Bs, n, h, 0, tid);          // overlaps with the slab work below
+    for (int k = 0; k < S - 1; ++k) {               // S-1 chunks in flight: they overlap with the slab work below
+      if (k < n_chunks) stage_chunk(f, As + k * kFChunk * Wp, Bs + k * kFChunk * Wp, n, h, k * kFChunk, tid);
+      cp_async_commit();
+    }
     // ---- a. masked upstream gradient and the saved slab ----
     for (int i = tid; i < O * W; i += kFThreads) {
       const int o = i / W, w = i % W;
@@ -231,12 +246,12 @@ __global__ void __launch_bounds__(kFThreads) corr_conv_relu_bwd_kernel(const Fus
       }
     }
     for (int k = 0; k < n_chunks; ++k) {
-      const int s = k & 1;
-      if (k + 1 < n_chunks) {
-        stage_chunk(f, As + (s ^ 1) * kFChunk * Wp, Bs + (s ^ 1) * kFChunk * Wp, n, h, (k + 1) * kFChunk, tid);
-        cp_async_wait<1>();
-      } else {
-        cp_async_wait<0>();
+      const int s = k % S;
+      {
+        const int kn = k + S - 1, sn = kn % S;
+        if (kn < n_chunks) stage_chunk(f, As + sn * kFChunk * Wp, Bs + sn * kFChunk * Wp, n, h, kn * kFChunk, tid);
+        cp_async_commit();
+        cp_async_wait_dyn(S - 1);
       }
       __syncthreads();
       if (worker) {
@@ -279,15 +294,25 @@ __global__ void __launch_bounds__(256) corr_conv_gw_reduce_kernel(const float* _
   gw[i] = s;
 }
 
-size_t fused_bwd_smem(int W, int O) {
+size_t fused_bwd_smem(int W, int O, int stages) {
   const int Wp = W + 16, n_og = kFThreads / W > 0 ? kFThreads / W : 1;
-  return sizeof(float) * ((size_t)4 * kFChunk * Wp + (size_t)O * (W + 1) + (size_t)W * 20 + (size_t)O * 20 + 17 * W +
+  return sizeof(float) * ((size_t)2 * stages * kFChunk * Wp + (size_t)O * (W + 1) + (size_t)W * 20 + (size_t)O * 20 + 17 * W +
                           (size_t)n_og * 17 * W);
+}
+size_t fused_fwd_smem(int W, int O, int stages) {
+  const int Wp = W + 16, G = kFThreads / (W / 2);
+  return sizeof(float) * ((size_t)2 * stages * kFChunk * Wp + (size_t)G * 17 * W + 17 * W + (size_t)O * 17);
+}
+int pick_stages(size_t (*need)(int, int, int), int W, int O) {
+  for (int s = kFStages; s >= 2; --s)
+    if (need(W, O, s) <= 220 * 1024) return s;
+  return 0;
 }
 
 bool fused_shape_ok(int C, int H, int W, int P, int O) {
+  // the backward keeps the masked (O, W) gradient of the row in shared memory next to at least two staging buffers
   return P == 17 && C >= 1 && H >= 1 && W >= 16 && W <= kFMaxW && W % 4 == 0 && O >= 1 && O <= 256 &&
-         fused_bwd_smem(W, O) <= 220 * 1024;   // the backward keeps the masked (O, W) gradient of the row in shared memory
+         pick_stages(fused_bwd_smem, W, O) >= 2 && pick_stages(fused_fwd_smem, W, O) >= 2;
 }
 
 void fill(FusedArgs* f, int B, int C, int H, int W, int O) {
@@ -309,7 +334,8 @@ int launch_corr_conv_relu_fwd(const float* a, const float* b, const float* wt, f
   FusedArgs f{};
   f.a = a, f.b = b, f.wt = wt, f.z = z, f.corr = corr;
   fill(&f, B, C, H, W, O);
-  const size_t smem = sizeof(float) * ((size_t)4 * kFChunk * f.Wp + (size_t)f.G * 17 * W + 17 * W + (size_t)O * 17);
+  f.stages = pick_stages(fused_fwd_smem, W, O);
+  const size_t smem = fused_fwd_smem(W, O, f.stages);
   PMT_CUDA_OK(cudaFuncSetAttribute(corr_conv_relu_fwd_kernel<17>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int rows = B * H;
   const int grid = rows < 2 * sm_count() ? rows : 2 * sm_count();
@@ -327,7 +353,8 @@ int launch_corr_conv_relu_bwd(const float* a, const float* b, const float* wt, c
   f.a = a, f.b = b, f.wt = wt, f.z = const_cast<float*>(z), f.corr = const_cast<float*>(corr), f.gz = gz;
   f.ga = ga, f.gb = gb, f.gw_part = gw_part;
   fill(&f, B, C, H, W, O);
-  const size_t smem = fused_bwd_smem(W, O);
+  f.stages = pick_stages(fused_bwd_smem, W, O);
+  const size_t smem = fused_bwd_smem(W, O, f.stages);
   PMT_CUDA_OK(cudaFuncSetAttribute(corr_conv_relu_bwd_kernel<17>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int rows = B * H;
   const int grid = rows < 2 * sm_count() ? rows : 2 * sm_count();

@@ -442,15 +442,26 @@ __global__ void __launch_bounds__(kRowThreads) warp_bwd_rows_kernel(const RowBwd
             for (int cc = 0; cc < nc; ++cc) dgo[i] = fmaf(sm.gs[cc * W4 + x], sm.is[cc * W4 + x1] - sm.is[cc * W4 + x0], dgo[i]);
           }
           if (need_img && !(warps_take_big && n_[i] > kBigBucket)) {
-            // bucket of destination x: entries b .. b+n-1; the first two inline, the (rare) rest in a loop
+            // bucket of destination x: entries b .. b+n-1; the first four inline and branch-free (smooth disparities give
+            // two per bucket, random ones rarely more than four), the rest in a loop
             const int b = b_[i], nb = n_[i];
-            const float v0 = nb > 0 ? sm.ev[b] : 0.f, v1 = nb > 1 ? sm.ev[b + 1] : 0.f;
-            const int w0 = nb > 0 ? sm.ew[b] : 0, w1 = nb > 1 ? sm.ew[b + 1] : 0;
-            for (int cc = 0; cc < nc; ++cc) {
+            float v_[4];
+            int w_[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              v_[j] = nb > j ? sm.ev[b + j] : 0.f;
+              w_[j] = nb > j ? (int)sm.ew[b + j] : 0;
+            }
+            float* o = a.gimg + ((int64_t)n * C + c0) * plane + (int64_t)h * W + x;
+            for (int cc = 0; cc < nc; ++cc, o += plane) {
               const float* g = sm.gs + cc * W4;
-              float acc = __fadd_rn(__fmul_rn(v0, g[w0]), __fmul_rn(v1, g[w1]));
-              for (int e = b + 2; e < b + nb; ++e) acc = __fadd_rn(acc, __fmul_rn(sm.ev[e], g[sm.ew[e]]));
-              st_cs(a.gimg + ((int64_t)n * C + c0 + cc) * plane + (int64_t)h * W + x, acc);
+              // selects, not multiplications by a zero weight: an absent entry must not turn an inf/nan of g[0] into a nan
+              float acc = nb > 0 ? __fmul_rn(v_[0], g[w_[0]]) : 0.f;
+              acc = nb > 1 ? __fadd_rn(acc, __fmul_rn(v_[1], g[w_[1]])) : acc;
+              acc = nb > 2 ? __fadd_rn(acc, __fmul_rn(v_[2], g[w_[2]])) : acc;
+              acc = nb > 3 ? __fadd_rn(acc, __fmul_rn(v_[3], g[w_[3]])) : acc;
+              for (int e = b + 4; e < b + nb; ++e) acc = __fadd_rn(acc, __fmul_rn(sm.ev[e], g[sm.ew[e]]));
+              st_cs(o, acc);
             }
           }
         }

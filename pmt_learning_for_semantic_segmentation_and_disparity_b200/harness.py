@@ -17,7 +17,8 @@ import torch.nn.functional as F
 from torch import nn
 
 from .correlation import CorrelationConvReLU, SpatialCorrelationSampler
-from .syncbn import PairedSyncBatchNorm, PeerExchange, pair_batchnorms  # noqa: F401  (re-exported: the harness API)
+from .syncbn import (PairedSyncBatchNorm, PeerExchange, pair_batchnorms,  # noqa: F401  (re-exported: the harness API)
+                     sync_batchnorms_to_peer)
 from .warp import apply_disparity, warp_blend
 
 
@@ -182,8 +183,9 @@ def build_training_step(world, batch_per_gpu: int = 4, h: int = 256, w: int = 51
         if paired_tower and sync_bn:
             model.pair_tower()
             if peer_bn and world.distributed:
-                # statistics of the paired BN layers travel over NVLink peer memory inside the kernels: no collective
-                # launch per layer (the remaining nn.SyncBatchNorm layers of the decoders keep NCCL)
+                # statistics of EVERY BN layer travel over NVLink peer memory inside the kernels: the paired tower layers
+                # and (merged=True: whole-batch statistics) the decoders' -- no collective launch per layer is left
+                sync_batchnorms_to_peer(model)
                 exchange = PeerExchange.attach(model)
         if world.distributed:
             model = nn.parallel.DistributedDataParallel(model, device_ids=[world.local_rank])

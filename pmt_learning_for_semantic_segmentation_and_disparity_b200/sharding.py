@@ -30,13 +30,15 @@ class World:
         return self.rank == 0
 
 
-def init_world(backend: str | None = None) -> World:
+def init_world(backend: str | None = None, force_group: bool = False) -> World:
     """Join the job described by RANK / LOCAL_RANK / WORLD_SIZE / MASTER_ADDR / MASTER_PORT (torchrun env).
-    Single process (no env) -> a 1-rank world without a process group."""
+    Single process (no env) -> a 1-rank world without a process group, unless force_group: then a 1-rank process group
+    is created so that a single GPU runs exactly the code path of N GPUs (DDP, SyncBatchNorm conversion, exchange kernels)
+    -- the N = 1 point of a scaling curve must be the same configuration as the N > 1 points."""
     ws = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", str(rank)))
-    if ws <= 1:
+    if ws <= 1 and not force_group:
         return World(0, 0, 1, None)
     if backend is None:
         backend = "nccl" if torch.cuda.is_available() else "gloo"

@@ -107,10 +107,10 @@ class _PairedSyncBNFusedFn(torch.autograd.Function):
             st = lib.pmt_bn_pair_apply_f32(U.ptr(x), U.ptr(gathered), int(world_size), U.ptr(weight), U.ptr(bias),
                                            U.ptr(running_mean), U.ptr(running_var), ctypes.c_float(momentum),
                                            ctypes.c_float(eps), U.ptr(out), U.ptr(save_mean), U.ptr(save_invstd), B, C, HW,
-                                           int(bool(relu)), U.stream_ptr(dev))
+                                           int(relu), U.stream_ptr(dev))
         U._lib.check(st, "pmt_bn_pair_apply_f32")
         ctx.save_for_backward(x, weight, bias, save_mean, save_invstd)
-        ctx.group, ctx.world_size, ctx.relu = group, world_size, int(bool(relu))
+        ctx.group, ctx.world_size, ctx.relu = group, world_size, int(relu)   # flags: bit 0 ReLU, bit 1 merged halves
         return out
 
     @staticmethod
@@ -154,6 +154,7 @@ class PeerExchange:
         self.ptr_table = ptr_table              # int64 device tensor [world]: base pointers of all ranks' buffers
         self._keepalive = keepalive
         self.cursor = 0                         # floats handed out so far (identical on all ranks)
+        self.wait = 1                           # producers wait for their peers inside the kernel (0: emulated ranks)
         dev = local.device
         self.err = torch.zeros(1, dtype=torch.int32, device=dev)
         self._counters = []
@@ -177,7 +178,7 @@ class PeerExchange:
         self.cursor += _round4(2 * self.world)
         if self.cursor > self.local.numel():
             raise RuntimeError("PeerExchange buffer too small")
-        counters = torch.zeros(2, dtype=torch.int32, device=self.local.device)   # [epoch, done]
+        counters = torch.zeros(4, dtype=torch.int32, device=self.local.device)   # [epoch, done, ready, -]
         self._counters.append(counters)
         return payload_off, flag_off, counters
 
@@ -205,7 +206,10 @@ class PeerExchange:
     def emulated(cls, world: int, floats: int, device):
         bufs = [torch.zeros(max(floats, 4), dtype=torch.float32, device=device) for _ in range(world)]
         table = torch.tensor([b.data_ptr() for b in bufs], dtype=torch.int64, device=device)
-        return [cls(world, r, bufs[r], table, keepalive=tuple(bufs)) for r in range(world)]
+        ranks = [cls(world, r, bufs[r], table, keepalive=tuple(bufs)) for r in range(world)]
+        for x in ranks:
+            x.wait = 0                          # one device runs the ranks one after the other: nobody may wait in a kernel
+        return ranks
 
     def _bind(self, module: nn.Module, group):
         for m in module.modules():
@@ -243,7 +247,7 @@ class _PairedSyncBNPeerFn(torch.autograd.Function):
         with torch.cuda.device(dev):
             st = lib.pmt_bn_pair_stats_peer_f32(U.ptr(x), vp(xch.ptr_table.data_ptr()), vp(xch.local.data_ptr()), xch.world,
                                                 xch.rank, f_pay, f_flag, vp(f_cnt.data_ptr()), vp(f_cnt.data_ptr() + 4),
-                                                vp(xch.err.data_ptr()), B, C, HW, U.stream_ptr(dev))
+                                                vp(xch.err.data_ptr()), xch.wait, B, C, HW, U.stream_ptr(dev))
             U._lib.check(st, "pmt_bn_pair_stats_peer_f32")
             out = torch.empty_like(x)
             save_mean = torch.empty(2 * C, device=dev, dtype=torch.float32)
@@ -252,10 +256,10 @@ class _PairedSyncBNPeerFn(torch.autograd.Function):
                                                 vp(f_cnt.data_ptr()), vp(xch.err.data_ptr()), U.ptr(weight), U.ptr(bias),
                                                 U.ptr(running_mean), U.ptr(running_var), ctypes.c_float(momentum),
                                                 ctypes.c_float(eps), U.ptr(out), U.ptr(save_mean), U.ptr(save_invstd), B, C,
-                                                HW, int(bool(relu)), U.stream_ptr(dev))
+                                                HW, int(relu), U.stream_ptr(dev))
             U._lib.check(st, "pmt_bn_pair_apply_peer_f32")
         ctx.save_for_backward(x, weight, bias, save_mean, save_invstd)
-        ctx.peer, ctx.relu = (xch, bwd), int(bool(relu))
+        ctx.peer, ctx.relu = (xch, bwd), int(relu)
         return out
 
     @staticmethod
@@ -278,7 +282,7 @@ class _PairedSyncBNPeerFn(torch.autograd.Function):
             st = lib.pmt_bn_pair_bwd_reduce_peer_f32(U.ptr(grad), U.ptr(x), U.ptr(save_mean), U.ptr(save_invstd),
                                                      vp(xch.ptr_table.data_ptr()), vp(xch.local.data_ptr()), xch.world, xch.rank,
                                                      b_pay, b_flag, vp(b_cnt.data_ptr()), vp(b_cnt.data_ptr() + 4),
-                                                     vp(xch.err.data_ptr()), U.ptr(gwb[0]), U.ptr(gwb[1]), B, C, HW,
+                                                     vp(xch.err.data_ptr()), xch.wait, U.ptr(gwb[0]), U.ptr(gwb[1]), B, C, HW,
                                                      U.ptr(weight), U.ptr(bias), ctx.relu, U.stream_ptr(dev))
             U._lib.check(st, "pmt_bn_pair_bwd_reduce_peer_f32")
             st = lib.pmt_bn_pair_bwd_apply_peer_f32(U.ptr(grad), U.ptr(x), U.ptr(save_mean), U.ptr(save_invstd), U.ptr(weight),
@@ -302,6 +306,8 @@ class PairedSyncBatchNorm(nn.BatchNorm2d):
 
     fused = True
     relu = False   # True: the ReLU that follows this BN is computed by the same kernels (pair_batchnorms sets it)
+    merged = False  # True: the two halves are ONE batch -- plain (Sync)BatchNorm semantics over the whole (even) batch, on
+                    # the same kernels and the same exchange (sync_batchnorms_to_peer converts the non-siamese layers)
     process_group = None
     peer = None    # (PeerExchange, forward slot, backward slot): statistics travel over NVLink peer memory, no collective
 
@@ -330,17 +336,20 @@ class PairedSyncBatchNorm(nn.BatchNorm2d):
                 raise NotImplementedError("PairedSyncBatchNorm(fused=True) needs a numeric momentum; momentum=None "
                                           "(cumulative average) is implemented by .fused = False")
             if track and self.num_batches_tracked is not None:
-                self.num_batches_tracked.add_(2)
+                self.num_batches_tracked.add_(1 if self.merged else 2)
             if x.data_ptr() % 16:
                 x = x.clone(memory_format=torch.contiguous_format)   # an offset view: the kernels read 16-byte vectors
+            flags = int(bool(self.relu)) | (2 if self.merged else 0)
             if self.peer is not None:
                 return _PairedSyncBNPeerFn.apply(x, self.weight, self.bias, self.running_mean if track else None,
                                                  self.running_var if track else None, self.eps,
-                                                 self.momentum if self.momentum is not None else 0.0, self.peer, self.relu)
+                                                 self.momentum if self.momentum is not None else 0.0, self.peer, flags)
             return _PairedSyncBNFusedFn.apply(x, self.weight, self.bias, self.running_mean if track else None,
                                               self.running_var if track else None, self.eps,
                                               self.momentum if self.momentum is not None else 0.0, self.process_group, ws,
-                                              self.relu)
+                                              flags)
+        if self.merged:
+            raise NotImplementedError("PairedSyncBatchNorm(merged=True) is implemented by the fused kernels only")
         if self.momentum is None and track:
             # cumulative moving average: the left call sees num_batches_tracked+1, the right call +2 (two calls of one BN)
             n = int(self.num_batches_tracked) if self.num_batches_tracked is not None else 0
@@ -390,4 +399,26 @@ def pair_batchnorms(module: nn.Module, fuse_relu: bool = False) -> nn.Module:
             setattr(module, name, new)
         else:
             pair_batchnorms(child, fuse_relu)
+    return module
+
+
+def sync_batchnorms_to_peer(module: nn.Module) -> nn.Module:
+    """Convert the remaining nn.SyncBatchNorm / BatchNorm2d layers below `module` (the non-siamese ones: decoders, heads)
+    into PairedSyncBatchNorm(merged=True): whole-batch statistics, i.e. what nn.SyncBatchNorm computes, but on the bn_pair
+    kernels -- so that `PeerExchange.attach` can route their statistics over NVLink peer memory as well and no BN layer of
+    the model launches a collective.  The per-GPU batch must be even (the kernels split it in two halves internally)."""
+    for name, child in list(module.named_children()):
+        if isinstance(child, PairedSyncBatchNorm):
+            continue
+        if isinstance(child, (nn.BatchNorm2d, nn.SyncBatchNorm)):
+            new = PairedSyncBatchNorm(child.num_features, child.eps, child.momentum, child.affine, child.track_running_stats)
+            new.weight, new.bias = child.weight, child.bias
+            new.training = child.training
+            new.running_mean, new.running_var, new.num_batches_tracked = (child.running_mean, child.running_var,
+                                                                          child.num_batches_tracked)
+            new.process_group = getattr(child, "process_group", None)
+            new.merged = True
+            setattr(module, name, new)
+        else:
+            sync_batchnorms_to_peer(child)
     return module

@@ -231,7 +231,7 @@ def test_bn_pair_peer_exchange_emulated_two_ranks():
             (f_pay, f_flag, f_cnt), _ = slots[r]
             st = lib.pmt_bn_pair_stats_peer_f32(U.ptr(xs[r]), vp(xch.ptr_table.data_ptr()), vp(xch.local.data_ptr()), world, r,
                                                 f_pay, f_flag, vp(f_cnt.data_ptr()), vp(f_cnt.data_ptr() + 4),
-                                                vp(xch.err.data_ptr()), B, C, HW, U.stream_ptr(DEV))
+                                                vp(xch.err.data_ptr()), 0, B, C, HW, U.stream_ptr(DEV))
             assert st == 0, U._lib.last_error()
         for r, xch in enumerate(ranks):
             (f_pay, f_flag, f_cnt), _ = slots[r]
@@ -248,7 +248,7 @@ def test_bn_pair_peer_exchange_emulated_two_ranks():
             st = lib.pmt_bn_pair_bwd_reduce_peer_f32(U.ptr(dys[r]), U.ptr(xs[r]), U.ptr(got[r][1]), U.ptr(got[r][2]),
                                                      vp(xch.ptr_table.data_ptr()), vp(xch.local.data_ptr()), world, r, b_pay,
                                                      b_flag, vp(b_cnt.data_ptr()), vp(b_cnt.data_ptr() + 4),
-                                                     vp(xch.err.data_ptr()), U.ptr(gw[0]), U.ptr(gw[1]), B, C, HW,
+                                                     vp(xch.err.data_ptr()), 0, U.ptr(gw[0]), U.ptr(gw[1]), B, C, HW,
                                                      U.ptr(weight), U.ptr(bias), 1, U.stream_ptr(DEV))
             assert st == 0, U._lib.last_error()
         for r, xch in enumerate(ranks):
