@@ -251,9 +251,10 @@ int pmt_bn_pair_bwd_apply_peer_f32(const float* dy, const float* x, const float*
 /* ---------------------------------------------------------------------------------------------
  * Host-buffer entry point for the headline workload (what a non-PyTorch caller of the reference's
  * sampler backend would bind): forward + backward of the 1 x P correlation on HOST tensors.
- * Copies in (in1,in2,gout), runs both kernels, copies out (out,gin1,gin2), batch item by batch
- * item through 3 device slots with separate H2D / compute / D2H streams (both PCIe directions and
- * the kernels overlap), then synchronises.  Host buffers should be pinned for full PCIe rate.
+ * Copies in (in1,in2,gout), runs both kernels, copies out (out,gin1,gin2), in row blocks of ~1/8
+ * batch item (image rows are independent) through 3 device slots with separate H2D / compute / D2H
+ * streams (both PCIe directions and the kernels overlap), then synchronises.  Host buffers should
+ * be pinned for full PCIe rate.
  * ------------------------------------------------------------------------------------------- */
 int pmt_corr1d_fwd_bwd_host_f32(const float* in1_host, const float* in2_host, const float* gout_host,
                                 float* out_host, float* gin1_host, float* gin2_host, int B, int C,

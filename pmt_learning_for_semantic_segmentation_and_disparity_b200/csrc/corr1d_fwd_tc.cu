@@ -451,17 +451,23 @@ corr1d_fwd_tca_kernel(const __grid_constant__ CUtensorMap tmL, const __grid_cons
       const int wt = tile % a.n_wtiles, h = (tile / a.n_wtiles) % a.H, n = tile / (a.n_wtiles * a.H);
       mbar_wait(tmem_full, (uint32_t)it & 1u);
       tc::fence_after_sync();
-      float vp[16], vc[16];
+      // software pipeline over the TMEM loads: block s+q+2 is requested before the staging stores of step s, so its
+      // latency is hidden behind them (vp = block s+q, vc = block s+q+1, vn = block s+q+2 in flight)
+      uint32_t vp[16], vc[16], vn[16];
       const uint32_t tcol = tmem_base + ((uint32_t)(32 * q) << 16) + (uint32_t)(a.delta + 16 * hsel);
-      tc::tmem_ld16(tcol + (uint32_t)(32 * q), vp);
+      tc::tmem_ld16_async(tcol + (uint32_t)(32 * q), vp);
+      tc::tmem_ld16_async(tcol + (uint32_t)(32 * (q + 1)), vc);
+      tc::tmem_ld_wait16(vp);
+      tc::tmem_ld_wait16(vc);
       const int r0 = (32 - lane + 16 * hsel) & 31;
       for (int s = 0; s < a.n_steps; ++s, ++gstep) {
         float* tile_s = reinterpret_cast<float*>(smem + a.tile_off + (gstep % a.n_bufs) * kStepBytes);
-        tc::tmem_ld16(tcol + (uint32_t)(32 * (s + q + 1)), vc);
-        if (s == a.n_steps - 1) {
+        if (s + 1 < a.n_steps) {
+          tc::tmem_ld16_async(tcol + (uint32_t)(32 * (s + q + 2)), vn);
+        } else {
           tc::fence_before_sync();
           __syncwarp();
-          if (lane == 0) mbar_arrive(tmem_empty);  // TMEM drained: the next tile's MMAs may start
+          if (lane == 0) mbar_arrive(tmem_empty);  // every block of this tile has been read: the next tile's MMAs may start
         }
         if (wid == 2 && lane == 0) {   // the store that last used this buffer has read it
           if (a.n_bufs == 3) tc::tma_store_wait_read<2>();
@@ -472,16 +478,19 @@ corr1d_fwd_tca_kernel(const __grid_constant__ CUtensorMap tmL, const __grid_cons
 #pragma unroll
         for (int j = 0; j < 16; ++j) {
           const int jj = 16 * hsel + j;
-          const float v = (jj >= lane) ? vp[j] : vc[j];
-          col[((r0 + j) & 31) * kTM] = v;        // staging row = plane - 32s = (jj - lane) mod 32
+          const uint32_t v = (jj >= lane) ? vp[j] : vc[j];
+          col[((r0 + j) & 31) * kTM] = __uint_as_float(v);   // staging row = plane - 32s = (jj - lane) mod 32
         }
-#pragma unroll
-        for (int j = 0; j < 16; ++j) vp[j] = vc[j];
         fence_proxy_async();                       // generic-proxy writes -> visible to the TMA store
         named_bar_sync(1, 32 * kTcaEpiWarps);
         if (wid == 2 && lane == 0) {
           tc::tma_store_4d(&tmO, tile_s, wt * kTM, h, kRowsPerStep * s, n);
           tc::tma_store_commit();
+        }
+        if (s + 1 < a.n_steps) {
+          tc::tmem_ld_wait16(vn);                  // vn has landed (its latency overlapped the stores above)
+#pragma unroll
+          for (int j = 0; j < 16; ++j) vp[j] = vc[j], vc[j] = vn[j];
         }
       }
     }
