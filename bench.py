@@ -35,11 +35,11 @@ UNIT = "pairs/s"
 N_SETS = 2  # rotating buffer sets (each 1.34 GB >> 126 MB L2)
 PREHEAT_S = 2.0  # seconds of the same load before the timed region (sustained clocks under the 1 kW power cap)
 DOMINANT_KERNEL = "corr1d_bwd_tc_kernel<3, 3>"
-FWD_KERNEL = "corr1d_fwd_tc_kernel<3>"
+FWD_KERNEL = "corr1d_fwd_tca_kernel<3>"
 # dram__bytes_read.sum + dram__bytes_write.sum of one launch of the dominant kernel at this exact workload, from the
 # committed ncu --set full capture (per launch; the kernel reads g once per gradient, hence > algorithmic bytes)
-NCU_DRAM_BYTES_BWD = 671_518_720 + 244_259_584
-NCU_SOURCE = "profiles/r01_ncu_corr_tc_v8.md (ncu --set full, corr1d_bwd_tc_kernel<3, 3>, B=4 headline workload)"
+NCU_DRAM_BYTES_BWD = 676_919_808 + 245_281_792
+NCU_SOURCE = "profiles/r02_ncu_corr.md (ncu --set full, corr1d_bwd_tc_kernel<3, 3>, B=4 headline workload)"
 
 
 def algorithmic_work(c=C, h=H, w=W, p=P):

@@ -22,17 +22,24 @@ KEYS = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum
         "smsp__average_warps_issue_stalled_mio_throttle_per_issue_active.ratio"]
 
 
-def main(rep, out):
-    raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+def main(rep, out, pick="first"):
+    if rep.endswith(".csv"):   # already exported with `ncu -i X.ncu-rep --page raw --csv`
+        raw = open(rep).read()
+    else:
+        raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(raw.splitlines()))
     hdr, units = rows[0], rows[1]
     ix = {h: i for i, h in enumerate(hdr)}
     seen = {}
     for r in rows[2:]:
         name = r[ix["Kernel Name"]].split("(")[0].split("::")[-1]
-        seen.setdefault(name, r)  # first captured launch of each kernel
+        if pick == "longest":     # several shapes per kernel in one capture: keep the longest launch
+            if name not in seen or float(r[ix["gpu__time_duration.sum"]].replace(",", "")) > float(seen[name][ix["gpu__time_duration.sum"]].replace(",", "")):
+                seen[name] = r
+        else:
+            seen.setdefault(name, r)  # first captured launch of each kernel
     with open(out, "w") as f:
-        f.write(f"# ncu --set full summary of `{rep}` (first captured launch per kernel)\n\n")
+        f.write(f"# ncu --set full summary of `{rep}` ({pick} captured launch per kernel)\n\n")
         f.write("| metric | " + " | ".join(seen) + " |\n|---|" + "---|" * len(seen) + "\n")
         for k in KEYS:
             if k in ix:
@@ -41,4 +48,4 @@ def main(rep, out):
 
 
 if __name__ == "__main__":
-    main(sys.argv[1], sys.argv[2])
+    main(*sys.argv[1:4])
