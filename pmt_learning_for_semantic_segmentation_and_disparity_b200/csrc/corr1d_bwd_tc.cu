@@ -40,7 +40,16 @@ struct BwdCfg {
   static constexpr int kGroups = kGroups_;
   static constexpr int kGroupWarps = 4;
   static constexpr int kBuilders = kGroupWarps * kGroups;
-  static constexpr int kThreads = 32 * (3 + kEpiWarps + kBuilders);  // band producer, MMA, 4 epilogue, builders, raw-g producer
+  // 3xTF32: two more warps split the landed feature band into hi / lo (they take the K chunks alternately).  The
+  // builders used to do it at the end of every chunk; a cycle-stamped profile of one CTA showed a builder group spending
+  // ~900 of its ~3800 cycles per chunk there (a barrier wait, 8 KB through LDS/STS, a proxy fence), and the rate of the
+  // kernel is kGroups chunks per such group cycle.  21 warps x 96 registers still fit the register file.
+  // Two teams take the chunks alternately (a ring a team waits on needs one slot per team: band_slots >= 2); with 2
+  // builder groups (wide bands: C = 128 is 16 KB per chunk) a team is two warps that split a chunk between them.
+  static constexpr int kSplitTeams = 2;
+  static constexpr int kSplitPer = kGroups_ == 2 ? 4 : 2;
+  static constexpr int kSplitWarps = kPasses == 3 ? kSplitTeams * kSplitPer : 0;
+  static constexpr int kThreads = 32 * (3 + kEpiWarps + kBuilders + kSplitWarps);  // band producer, MMA, 4 epilogue, builders, raw-g producer, band split
 };
 constexpr int kBox0Bytes = 32 * kTM * 4;          // mode 0: 32 rows of g x 128 columns (16 KB)
 constexpr int kRawRows1 = 160;                    // mode 1: rows of a raw block (>= 128+32-1)
@@ -150,7 +159,8 @@ corr1d_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmIn1, const __grid_con
   uint64_t* raw_empty = raw_full + 8;
   uint64_t* tmem_full = raw_empty + 8;
   uint64_t* tmem_empty = tmem_full + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+  uint64_t* band_split = tmem_empty + 2;   // 3xTF32: lo half of a band slot written (one split warp per chunk)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(band_split + kMaxBandSlots);
 
 
   const int mode = (int)blockIdx.x < a.n_cta0 ? 0 : 1;
@@ -172,12 +182,12 @@ corr1d_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmIn1, const __grid_con
   const int band_bytes = a.Cbox * 128;
   int n_my = (a.n_tiles - cta_in_mode + ctas_of_mode - 1) / ctas_of_mode;  // tiles of this CTA
   if (PMT_DBG(a, (mode == 0 ? 4096 : 2048))) n_my = 0;   // ablation: run one gradient only
-  const int G = n_my * a.NKC;                                                            // chunks of this CTA
 
   if (tid == 0) {
     for (int s = 0; s < kMaxBandSlots; ++s) {
       mbar_init(&band_full[s], 1);
       mbar_init(&band_empty[s], 1);
+      mbar_init(&band_split[s], BwdCfg<kPasses, kGroups>::kSplitPer);
     }
     for (int s = 0; s < kMaxGdSlots; ++s) {
       mbar_init(&gd_built[s], kGroupWarps);
@@ -295,6 +305,7 @@ corr1d_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmIn1, const __grid_con
         for (int k = 0; k < a.NKC; ++k) {
           PWAIT(1, &gd_built[gs], gph);
           if (kPasses == 1) PWAIT(2, &band_full[bs], bph);
+          else PWAIT(2, &band_split[bs], bph);   // hi landed (TMA) and lo written (split warps)
           tc::fence_after_sync();
           const uint64_t dB = dB0 + (uint64_t)(b_step * (uint32_t)bs);
           const uint32_t ta = tmem_base + (uint32_t)(a.a_base + gs * a.aslot_cols);
@@ -336,6 +347,38 @@ corr1d_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmIn1, const __grid_con
           if (++bs == m.band_slots) bs = 0, bph ^= 1u;
         }
       }
+    }
+  } else if (wid > 2 + kEpiWarps + kBuilders) {
+    // ===== band split (3xTF32): lo = x - trunc_tf32(x) of each landed feature band chunk, written next to it
+    // (position-wise, layout agnostic).  Team t takes chunks t, t + 2, ... =====
+    constexpr int kTeams = BwdCfg<kPasses, kGroups>::kSplitTeams, kPer = BwdCfg<kPasses, kGroups>::kSplitPer;
+    const int j = wid - (3 + kEpiWarps + kBuilders);
+    const int team = j / kPer, member = j % kPer;
+    const int G = n_my * a.NKC;
+    const int nch = band_bytes / 16;
+    int bs = team % m.band_slots;
+    uint32_t bph = (uint32_t)(team / m.band_slots) & 1u;
+    for (int g = team; g < G; g += kTeams) {
+      PWAIT(2, &band_full[bs], bph);
+      unsigned char* sb = band_ring + (size_t)bs * a.band_slot_bytes;
+      if (!PMT_DBG(a, 32)) {
+        for (int base = 32 * member + lane; base < nch; base += 8 * 32 * kPer) {   // 8 loads in flight per thread
+          float4 x[8];
+#pragma unroll
+          for (int u = 0; u < 8; ++u)
+            if (base + 32 * kPer * u < nch) x[u] = *reinterpret_cast<const float4*>(sb + 16 * (base + 32 * kPer * u));
+#pragma unroll
+          for (int u = 0; u < 8; ++u)
+            if (base + 32 * kPer * u < nch)
+              *reinterpret_cast<float4*>(sb + a.band_lo_off + 16 * (base + 32 * kPer * u)) =
+                  make_float4(lo_tf32(x[u].x), lo_tf32(x[u].y), lo_tf32(x[u].z), lo_tf32(x[u].w));
+        }
+      }
+      fence_proxy_async();   // generic-proxy writes -> visible to the tensor core's async-proxy reads
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&band_split[bs]);
+      bs += kTeams;
+      while (bs >= m.band_slots) bs -= m.band_slots, bph ^= 1u;
     }
   } else if (wid < 2 + kEpiWarps) {
     // ===== epilogue: TMEM -> coalesced global stores =====
@@ -385,19 +428,20 @@ corr1d_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmIn1, const __grid_con
     const int gw = ((bw >> 2) / kGroups) * 4 + (bw & 3);  // index inside the group, 0..kGroupWarps-1
     // running ring positions for the chunks this warp visits (g = grp, grp+2, ...): slot, and the phase parity seen
     // by a consumer-side wait (full/built); producer-side waits (empty) use the opposite parity
-    int g = 0;
-    int gs = grp % m.a_slots, bs = grp % m.band_slots, rs = grp % m.raw_slots;
-    uint32_t gph = (uint32_t)(grp / m.a_slots) & 1u, bph = (uint32_t)(grp / m.band_slots) & 1u,
-             rph = (uint32_t)(grp / m.raw_slots) & 1u;
+    int g = grp;   // chunk index (only the profiling build reads it)
+    int gs = grp % m.a_slots, rs = grp % m.raw_slots;
+    uint32_t gph = (uint32_t)(grp / m.a_slots) & 1u, rph = (uint32_t)(grp / m.raw_slots) & 1u;
     auto advance2 = [](int& slot, uint32_t& ph, int n) {
       slot += kGroups;
       while (slot >= n) slot -= n, ph ^= 1u;
     };
-    for (int i = 0; i < n_my; ++i) {
-      int boxes_ready = 0;
-      int next_rel = 0;                  // mode 0: boxes are handed back to the producer in increasing order
-      for (int k = 0; k < a.NKC; ++k, ++g) {
-        if (g % kGroups != grp) continue;
+    // The group walks its own chunks g = grp, grp + kGroups, ... directly as (tile i, chunk k) with a carry (NKC >= 4 >
+    // kGroups): a loop over every k that skipped the other groups' chunks cost a quarter of the builders' time in
+    // loop control and branch resolution (ncu source view, profiles/r02_ncu_corr.md).
+    int boxes_ready = 0;
+    int next_rel = 0;                    // mode 0: boxes are handed back to the producer in increasing order
+    for (int i = 0, k = grp; i < n_my;) {
+      {
         unsigned char* sa = gd_ring + (size_t)gs * a.gd_slot_bytes;
         if (mode == 0) {
           // rows p <= 32k+31-delta are needed: boxes 0..k of this tile's [P][128] slice
@@ -417,14 +461,18 @@ corr1d_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmIn1, const __grid_con
             const int xl = 32 * q + lane;
             const int pb = kKC * k + sub * kCols - m.delta - xl;  // p of column jj = sub*kCols + t is pb + t
             const uint32_t ta = tmem_base + ((uint32_t)(32 * q) << 16) + (uint32_t)(a.a_base + gs * a.aslot_cols + sub * kCols);
+            // slice row = min(plane + 1, P + 1) (planes outside [0, P) hit a zero row), computed on byte offsets into the
+            // slice so that an element costs one add-min and one LDS: offset = 4 xl + 512 row; 4 xl < 512, so a row
+            // below 0 wraps the unsigned offset far above the limit and is clamped like a row above P
+            const uint32_t lane_off = (uint32_t)xl * 4u;
+            const uint32_t lim_off = lane_off + ((uint32_t)a.P + 1u) * (kTM * 4u);
 #pragma unroll
             for (int c0 = 0; c0 < kCols; c0 += 16) {
               float w[16];
-              const float* col = Gt + xl;
-              const unsigned pu1 = (unsigned)(pb + c0 + 1), Pp1 = (unsigned)a.P + 1u;
+              const uint32_t o0 = lane_off + (uint32_t)(pb + c0 + 1) * (kTM * 4u);
 #pragma unroll
-              for (int t = 0; t < 16; ++t)   // slice row = min(plane + 1, P + 1): planes outside [0, P) hit a zero row
-                w[t] = col[min(pu1 + (unsigned)t, Pp1) * kTM];
+              for (int t = 0; t < 16; ++t)
+                w[t] = *reinterpret_cast<const float*>(smem + min(o0 + (uint32_t)t * (kTM * 4u), lim_off));
               if PMT_DBG(a, 4) {
 #pragma unroll
                 for (int t = 0; t < 16; ++t) w[t] = 0.f;
@@ -436,8 +484,10 @@ corr1d_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmIn1, const __grid_con
                 tc::tmem_st16(ta + 32 + c0, w);
               }
             }
+            { PSEC_BEGIN();
             tc::tmem_st_wait();
             tc::fence_before_sync();
+            PSEC_END(1); }
           } else {
 #pragma unroll
             for (int task = gw; task < 32; task += kGroupWarps) {   // 32 warp tasks per chunk: (16-byte column c4, 32-row block xb)
@@ -457,19 +507,6 @@ corr1d_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmIn1, const __grid_con
           }
           PSEC_END(0); }
           if (gw == 0) PTRACE(2 + grp, g, 3);
-          // hand back every box this warp will not read again (it visits chunks k, k+2, ...): box b is last used by
-          // chunk min(NKC-1, b+koff), so it is dead for this warp once k >= that chunk - 1
-          __syncwarp();
-          if (lane == 0) {
-            const bool last_visit = k + kGroups >= a.NKC;
-            while (next_rel < a.n_gboxes) {
-              int kl = next_rel + m.koff;
-              if (kl > a.NKC - 1) kl = a.NKC - 1;
-              if (!(kl <= k + kGroups - 1 || last_visit)) break;
-              mbar_arrive(&raw_empty[next_rel]);
-              ++next_rel;
-            }
-          }
         } else {
           const int slot = rs;
           if (gw == 0) PTRACE(2 + grp, g, 0);
@@ -479,7 +516,50 @@ corr1d_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmIn1, const __grid_con
           if (gw == 0) PTRACE(2 + grp, g, 2);
           const float* raw = reinterpret_cast<const float*>(smem + slot * kRawSlot1);
           { PSEC_BEGIN();
-          if (!PMT_DBG(a, 4)) {
+          if (m.tmem_a) {
+            // A operand straight into TMEM (thread = Gd row xl = TMEM lane, registers = the 32 band columns of the chunk):
+            // Gd[xl][jj] = raw[r = xl + 31 - jj][jj].  The raw block is a 128-byte-swizzled TMA box ([160 rows][32 floats]),
+            // so element (r, jj) sits at byte r*128 + (((jj >> 2) ^ (r & 7)) << 4) + 4*(jj & 3): for one jj the 32 lanes of
+            // a warp read 32 consecutive rows, i.e. every 16-byte slot of the row 4 times -- 4-way bank conflicts, but
+            // no shared->shared copy (1 LDS + 2 STS per element), no Gd ring in shared memory (96 KB that now hold a
+            // deeper raw ring) and no A-operand fetches by the MMA (32 KB per chunk).  With jj = 4 mm + n:
+            // r & 7 = ((xl + 31 - n) & 7) ^ (4 (mm & 1)), so the offset is base_n - 512 mm + ((K_mm << 4) ^ e_n) with four
+            // per-thread constants base_n, e_n and compile-time K_mm = mm ^ 4 (mm & 1).
+            const int q = wid & 3;
+            const int xl = 32 * q + lane;
+            const uint32_t ta = tmem_base + ((uint32_t)(32 * q) << 16) + (uint32_t)(a.a_base + gs * a.aslot_cols);
+            const unsigned char* rawb = smem + slot * kRawSlot1;
+            uint32_t base_n[4], e_n[4];
+#pragma unroll
+            for (int n = 0; n < 4; ++n) {
+              base_n[n] = (uint32_t)((xl + 31 - n) * 128 + 4 * n);
+              e_n[n] = (uint32_t)(((xl + 31 - n) & 7) << 4);
+            }
+#pragma unroll
+            for (int c0 = 0; c0 < kKC; c0 += 16) {
+              float w[16];
+#pragma unroll
+              for (int t = 0; t < 16; ++t) {
+                const int jj = c0 + t, mm = jj >> 2, n = jj & 3;
+                const uint32_t km = (uint32_t)((mm ^ (4 * (mm & 1))) << 4);
+                w[t] = *reinterpret_cast<const float*>(rawb + (base_n[n] - (uint32_t)(512 * mm) + (km ^ e_n[n])));
+              }
+              if PMT_DBG(a, 4) {
+#pragma unroll
+                for (int t = 0; t < 16; ++t) w[t] = 0.f;
+              }
+              tc::tmem_st16(ta + c0, w);
+              if (kPasses == 3) {
+#pragma unroll
+                for (int t = 0; t < 16; ++t) w[t] = lo_tf32(w[t]);
+                tc::tmem_st16(ta + 32 + c0, w);
+              }
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&raw_empty[slot]);   // every value of the block is in registers / on its way to TMEM
+            tc::tmem_st_wait();
+            tc::fence_before_sync();
+          } else if (!PMT_DBG(a, 4)) {
             // 32 warp tasks per chunk (4 Gd rows x 32 columns, lane = column); this warp takes tasks gw, gw+G, ...
             // All loads are issued before the first store so the LDS latency is paid once per chunk, not per row.
             constexpr int kTasks = 32 / kGroupWarps;
@@ -503,44 +583,32 @@ corr1d_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmIn1, const __grid_con
               }
           }
           PSEC_END(0); }
-          __syncwarp();
-          if (lane == 0) mbar_arrive(&raw_empty[slot]);
-        }
-        if (kPasses == 3) {
-          // split the landed feature band chunk into hi / lo (position-wise, layout agnostic)
-          if (gw == 0) PTRACE(2 + grp, g, 4);
-          PWAIT(2, &band_full[bs], bph);
-          if (gw == 0) PTRACE(2 + grp, g, 5);
-          PSEC_BEGIN();
-          unsigned char* sb = band_ring + (size_t)bs * a.band_slot_bytes;
-          const int nch = band_bytes / 16;
-          if (!PMT_DBG(a, 32)) {
-            constexpr int kStride = kGroupWarps * 32;
-            const int c0 = gw * 32 + lane;
-            for (int cb = c0; cb < nch; cb += 2 * kStride) {   // 2 loads in flight (C=64: one round)
-              float4 x[2];
-#pragma unroll
-              for (int u = 0; u < 2; ++u)
-                if (cb + u * kStride < nch) x[u] = *reinterpret_cast<const float4*>(sb + 16 * (cb + u * kStride));
-#pragma unroll
-              for (int u = 0; u < 2; ++u)
-                if (cb + u * kStride < nch)
-                  *reinterpret_cast<float4*>(sb + a.band_lo_off + 16 * (cb + u * kStride)) =
-                      make_float4(lo_tf32(x[u].x), lo_tf32(x[u].y), lo_tf32(x[u].z), lo_tf32(x[u].w));
-            }
+          if (!m.tmem_a) {
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&raw_empty[slot]);
           }
-          PSEC_END(2);
         }
         { PSEC_BEGIN();
-        fence_proxy_async();
+        if (!m.tmem_a) fence_proxy_async();   // shared-memory Gd: generic-proxy writes -> async-proxy (MMA) reads
         __syncwarp();
         if (lane == 0) mbar_arrive(&gd_built[gs]);
         PSEC_END(3); }
+        if (mode == 0) {
+          // Hand back every box of the g slice this warp will not read again -- after the A operand has been announced,
+          // so the releases are off the path to the MMA.  Box b is last used by chunk min(NKC-1, b+koff): boxes
+          // b <= k + kGroups - 1 - koff are dead for this warp, and on its last visit of the tile all of them are.
+          const int target = (k + kGroups >= a.NKC) ? a.n_gboxes : min(a.n_gboxes, k + kGroups - m.koff);
+          if (lane == 0)
+            for (int b = next_rel; b < target; ++b) mbar_arrive(&raw_empty[b]);
+          if (target > next_rel) next_rel = target;
+        }
         if (gw == 0) PTRACE(2 + grp, g, 6);
         advance2(gs, gph, m.a_slots);
-        advance2(bs, bph, m.band_slots);
         advance2(rs, rph, m.raw_slots);
       }
+      g += kGroups;
+      k += kGroups;
+      if (k >= a.NKC) k -= a.NKC, ++i, boxes_ready = 0, next_rel = 0;
     }
   }
 
@@ -597,13 +665,14 @@ int fill_args(TcBwdArgs* a, int C, int H, int W, int P, int passes, int groups) 
   for (int md = 0; md < 2; ++md) {
     TcBwdMode& m = a->m[md];
     // every ring a builder group waits on needs at least one slot per group (parity waits tolerate one phase of lead)
-    m.tmem_a = (md == 0 && want_tmem_a && tmem_slots >= groups) ? 1 : 0;
+    m.tmem_a = (want_tmem_a && tmem_slots >= groups && (md == 0 || PMT_ENV_INT("PMT_BWD_TMEM_A1", 1) != 0)) ? 1 : 0;
     int gd_bytes = 0;
     if (md == 0) {
       m.raw_slots = a->n_gboxes;
       m.gd_off = round_up(raw0 + 2 * kTM * 4, 1024);   // + the zero rows before plane 0 and after the last box
     } else {
-      m.raw_slots = groups < 3 ? kMaxRawSlots1 : groups;   // 3 groups: 3 raw + 3 Gd slots fit, 4 + 3 do not
+      if (m.tmem_a) m.raw_slots = 6;   // no Gd ring in shared memory: two raw blocks in flight per builder group
+      else m.raw_slots = groups < 3 ? kMaxRawSlots1 : groups;   // 3 groups: 3 raw + 3 Gd slots fit, 4 + 3 do not
       m.gd_off = round_up(m.raw_slots * kRawSlot1, 1024);
     }
     if (m.tmem_a) {
@@ -652,7 +721,7 @@ int launch_corr1d_bwd_tc(const float* in1, const float* in2, const float* gout, 
   if (int e = make_tmap_nchw_ex(&tm1, in1, B, C, H, W, kKC, a.Cbox, 1)) return e;
   if (int e = make_tmap_nchw_ex(&tm2, in2, B, C, H, W, kKC, a.Cbox, 1)) return e;
   if (int e = make_tmap_nchw_ex(&tmG0, gout, B, P, H, W, kTM, 32, 0)) return e;
-  if (int e = make_tmap_nchw_ex(&tmG1, gout, B, P, H, W, kKC, kRawRows1, 0)) return e;
+  if (int e = make_tmap_nchw_ex(&tmG1, gout, B, P, H, W, kKC, kRawRows1, a.m[1].tmem_a ? 1 : 0)) return e;
   const int smem_bytes = a.bar_off + 1024;
   const int64_t tiles = (int64_t)B * H * a.n_xtiles;
   PMT_CHECK_ARG(tiles < (1ll << 31), "corr1d tc bwd: too many tiles");
@@ -662,8 +731,9 @@ int launch_corr1d_bwd_tc(const float* in1, const float* in2, const float* gout, 
   const int sms = sm_count();
   int64_t n_cta = 2 * tiles < sms ? 2 * tiles : sms;
   if (n_cta < 2) n_cta = 2;
-  // measured optimum at the headline shape: an even split with 3 builder groups, 72 of 148 with 2
-  int n0 = (int)(n_cta * (a.m[0].tmem_a && groups == 2 && passes == 3 ? 0.4865 : 0.5) + 0.5);
+  // measured optimum at the headline shape (both A operands in TMEM): 72 of 148 SMs for gin1 -- its builders read the
+  // resident g slice conflict-free, gin2's read the swizzled raw blocks with 4-way bank conflicts
+  int n0 = (int)(n_cta * (a.m[0].tmem_a && a.m[1].tmem_a && passes == 3 ? 0.4865 : 0.5) + 0.5);
   if (const int e = PMT_ENV_INT("PMT_BWD_SPLIT", 0)) n0 = e;  // tuning knob
   if (n0 < 1) n0 = 1;
   if (n0 > n_cta - 1) n0 = (int)n_cta - 1;

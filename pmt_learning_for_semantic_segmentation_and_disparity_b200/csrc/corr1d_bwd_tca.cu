@@ -81,6 +81,7 @@ struct TcaArgs {
   int c1;              // mode 1: p = x + c1 - j
   int e0;              // mode 1: slice column of lane x in plane p is x + 3 - (p & 3) + e0
   int r;               // (P-1)/2
+  int only_mode;       // development builds: -1 = both gradients, 0 / 1 = run that gradient only
 };
 
 __device__ __forceinline__ float lo_tf32(float x) {
@@ -144,7 +145,10 @@ corr1d_bwd_tca_kernel(const __grid_constant__ CUtensorMap tmIn1, const __grid_co
 
   const int tid = threadIdx.x, wid = tid >> 5, lane = tid & 31;
   const int band_bytes = a.Cbox * 128;
-  const int n_my = (a.n_tiles - cta_in_mode + ctas_of_mode - 1) / ctas_of_mode;  // tiles of this CTA
+  int n_my = (a.n_tiles - cta_in_mode + ctas_of_mode - 1) / ctas_of_mode;  // tiles of this CTA
+#ifdef PMT_DEV_KNOBS
+  if (a.only_mode >= 0 && a.only_mode != mode) n_my = 0;   // development builds: time one gradient alone
+#endif
   constexpr bool three = kPasses == 3;
 
   if (tid == 0) {
@@ -547,6 +551,7 @@ int launch_corr1d_bwd_tca(const float* in1, const float* in2, const float* gout,
   if (n0 < 1) n0 = 1;
   if (n0 > n_cta - 1) n0 = (int)n_cta - 1;
   a.n_cta0 = n0;
+  a.only_mode = PMT_ENV_INT("PMT_TCA_ONLY", -1);
   if (passes == 3) {
     PMT_CUDA_OK(cudaFuncSetAttribute(corr1d_bwd_tca_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
     corr1d_bwd_tca_kernel<3><<<dim3((unsigned)n_cta), kThreads, smem_bytes, st>>>(tm1, tm2, tmG0, tmG1, gin1, gin2, a, g_bwd_prof);

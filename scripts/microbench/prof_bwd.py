@@ -2,7 +2,8 @@ import ctypes, sys, os
 import torch
 sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", ".."))
 import pmt_learning_for_semantic_segmentation_and_disparity_b200 as pmt
-lib = pmt.load_library(); dev = torch.device("cuda:0")
+lib = ctypes.CDLL(os.environ["PMT_PROF_LIB"]) if os.environ.get("PMT_PROF_LIB") else pmt.load_library()  # a -DPMT_BWD_PROFILE build
+dev = torch.device("cuda:0")
 vp = lambda t: ctypes.c_void_p(t.data_ptr())
 B, C, H, W, P = 4, 64, 256, 512, 192
 L = torch.randn(B, C, H, W, device=dev); R = torch.randn(B, C, H, W, device=dev); G = torch.randn(B,1,P,H,W, device=dev)
