@@ -39,7 +39,7 @@ DOMINANT_KERNEL = "corr1d_bwd_tc_kernel<3, 3>"
 FWD_KERNEL = "corr1d_fwd_tca_kernel<3>"
 # dram__bytes_read.sum + dram__bytes_write.sum of one launch of the dominant kernel at this exact workload, from the
 # committed ncu --set full capture (per launch; the kernel reads g once per gradient, hence > algorithmic bytes)
-NCU_DRAM_BYTES_BWD = 676_919_808 + 245_281_792
+NCU_DRAM_BYTES_BWD = 671_483_392 + 245_887_488
 NCU_SOURCE = "profiles/r02_ncu_corr.md (ncu --set full, corr1d_bwd_tc_kernel<3, 3>, B=4 headline workload)"
 
 

@@ -6,18 +6,25 @@
 //   D[x (M=128 TMEM lanes)][c (N=C columns)] = sum over the band (K = 32*NKC columns, 320 for P=192).
 // Persistent CTAs (one per SM, half of them per gradient) walk tiles with every stage of the pipeline
 // running ahead across tile boundaries:
-//   * warp 0 and the last warp (TMA producers): the feature band = B operand (rows c, K contiguous along w -> K-major),
-//     one 128-byte-swizzled [C][32] box per K chunk into a deep ring; raw g into a second ring -- mode 0: the
-//     tile's [P][128] slice as 32-row boxes (a box is recycled for the next tile as soon as its last
-//     chunk is built), mode 1: one [160][32] block per chunk (OOB rows/columns zero-filled by TMA);
-//   * warps 6.. (builders, groups of 4 warps that take the K chunks round-robin; 3 groups when three A slots fit,
-//     else 2): mode 0 writes the A operand Gd straight into TMEM (tcgen05.st: thread = Gd row, conflict-free column
-//     reads of the resident g slice), mode 1 re-lays raw g out shared->shared into the swizzled K-major A operand
-//     (all loads of a chunk before the first store); for 3xTF32 they write hi and lo copies and split the band;
-//   * warp 1 issues tcgen05.mma kind::tf32 (M=128, N=C, K=8; hi*hi + hi*lo + lo*hi for 3xTF32) into one
+//   * warp 0 and the warp after the builders (TMA producers): the feature band = B operand (rows c, K contiguous along
+//     w -> K-major), one 128-byte-swizzled [C][32] box per K chunk into a deep ring; raw g into a second ring -- mode 0:
+//     the tile's [P][128] slice as 32-row boxes (a box is recycled for the next tile as soon as its last chunk is
+//     built), mode 1: one 128-byte-swizzled [160][32] block per chunk (OOB rows/columns zero-filled by TMA), 6 deep;
+//   * builder warps (groups of 4 warps, one per TMEM lane quarter, that take the K chunks round-robin; 3 groups when
+//     the rings fit, else 2): both modes write the A operand Gd straight into TMEM when the columns are there (C <= 64
+//     for 3xTF32; tcgen05.st: thread = Gd row, registers = the 32 band columns of the chunk, hi = raw fp32 and
+//     lo = x - trunc_tf32(x)) with conflict-free reads -- mode 0: column reads of the resident g slice; mode 1: the
+//     diagonal of the swizzled raw block in a rotated column order, rotated back in registers.  Without TMEM room
+//     (C = 128 with 3xTF32) they re-lay raw g out shared->shared into the swizzled K-major A operand instead;
+//   * two teams of band-split warps (3xTF32) write lo = x - trunc_tf32(x) of every landed band chunk next to it;
+//   * warp 1 issues tcgen05.mma kind::tf32 (M=128, N=C, K=8; A_hi x [B_hi;B_lo] + A_lo x B_hi for 3xTF32) into one
 //     of two TMEM accumulators and commits to the mbarriers that recycle the rings;
 //   * warps 2-5 (epilogue) drain the other accumulator with tcgen05.ld and store gin[c][x] directly:
 //     a warp writes 32 consecutive columns of one channel per instruction (coalesced 128 bytes).
+// What bounds it (cycle-stamped per-warp profile, -DPMT_BWD_PROFILE): not DRAM, not the tensor pipe (45 % active), but
+// the latency chain of a builder group's chunk (barrier waits of ~200 cycles each, LDS -> tcgen05.st -> wait::st, fence,
+// arrive): the rate is `groups` chunks per chain, so everything that is not the build itself was moved off the
+// builders (band split -> own warps, box releases -> after the A operand is announced).
 #include <stdlib.h>
 
 #include "tc_common.cuh"
@@ -519,22 +526,28 @@ corr1d_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmIn1, const __grid_con
           if (m.tmem_a) {
             // A operand straight into TMEM (thread = Gd row xl = TMEM lane, registers = the 32 band columns of the chunk):
             // Gd[xl][jj] = raw[r = xl + 31 - jj][jj].  The raw block is a 128-byte-swizzled TMA box ([160 rows][32 floats]),
-            // so element (r, jj) sits at byte r*128 + (((jj >> 2) ^ (r & 7)) << 4) + 4*(jj & 3): for one jj the 32 lanes of
-            // a warp read 32 consecutive rows, i.e. every 16-byte slot of the row 4 times -- 4-way bank conflicts, but
-            // no shared->shared copy (1 LDS + 2 STS per element), no Gd ring in shared memory (96 KB that now hold a
-            // deeper raw ring) and no A-operand fetches by the MMA (32 KB per chunk).  With jj = 4 mm + n:
-            // r & 7 = ((xl + 31 - n) & 7) ^ (4 (mm & 1)), so the offset is base_n - 512 mm + ((K_mm << 4) ^ e_n) with four
-            // per-thread constants base_n, e_n and compile-time K_mm = mm ^ 4 (mm & 1).
+            // so element (r, jj) sits at byte r*128 + (((jj >> 2) ^ (r & 7)) << 4) + 4*(jj & 3).  Read in natural order
+            // (all lanes the same jj) the 32 consecutive rows of a warp hit every 16-byte slot 4 times: 4-way bank
+            // conflicts (ncu: half of the kernel's shared wavefronts).  Instead lane l reads, in instruction (mm, n), the
+            // column jj = 4 mm + ((n + h) & 3) with h = l >> 3: the 8 lanes of one h cover the 8 slots at one 4-byte
+            // position, the four h the four positions -- conflict-free -- and each group of 4 registers is rotated back
+            // by h afterwards (two selects per element).  With jj = 4 mm + c: r & 7 = ((xl + 31 - c) & 7) ^ (4 (mm & 1)),
+            // so the offset is base - 512 mm + ((K_mm << 4) ^ e) with per-thread constants base, e (one pair per n) and
+            // compile-time K_mm = mm ^ 4 (mm & 1).  No shared->shared copy (1 LDS + 2 STS per element before), no Gd ring
+            // in shared memory (96 KB that now hold a deeper raw ring), no A-operand fetches by the MMA (32 KB / chunk).
             const int q = wid & 3;
             const int xl = 32 * q + lane;
+            const int h = lane >> 3;
             const uint32_t ta = tmem_base + ((uint32_t)(32 * q) << 16) + (uint32_t)(a.a_base + gs * a.aslot_cols);
             const unsigned char* rawb = smem + slot * kRawSlot1;
             uint32_t base_n[4], e_n[4];
 #pragma unroll
             for (int n = 0; n < 4; ++n) {
-              base_n[n] = (uint32_t)((xl + 31 - n) * 128 + 4 * n);
-              e_n[n] = (uint32_t)(((xl + 31 - n) & 7) << 4);
+              const int c = (n + h) & 3;                 // the column (within a group of 4) this lane reads in slot n
+              base_n[n] = (uint32_t)((xl + 31 - c) * 128 + 4 * c);
+              e_n[n] = (uint32_t)(((xl + 31 - c) & 7) << 4);
             }
+            const bool rot1 = (h & 1) != 0, rot2 = (h & 2) != 0;
 #pragma unroll
             for (int c0 = 0; c0 < kKC; c0 += 16) {
               float w[16];
@@ -543,6 +556,14 @@ corr1d_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmIn1, const __grid_con
                 const int jj = c0 + t, mm = jj >> 2, n = jj & 3;
                 const uint32_t km = (uint32_t)((mm ^ (4 * (mm & 1))) << 4);
                 w[t] = *reinterpret_cast<const float*>(rawb + (base_n[n] - (uint32_t)(512 * mm) + (km ^ e_n[n])));
+              }
+              // w[4 g + n] holds column 4 g + ((n + h) & 3): rotate every group of 4 back by h
+#pragma unroll
+              for (int gq = 0; gq < 16; gq += 4) {
+                const float a0 = rot1 ? w[gq + 3] : w[gq + 0], a1 = rot1 ? w[gq + 0] : w[gq + 1];
+                const float a2 = rot1 ? w[gq + 1] : w[gq + 2], a3 = rot1 ? w[gq + 2] : w[gq + 3];
+                w[gq + 0] = rot2 ? a2 : a0, w[gq + 1] = rot2 ? a3 : a1;
+                w[gq + 2] = rot2 ? a0 : a2, w[gq + 3] = rot2 ? a1 : a3;
               }
               if PMT_DBG(a, 4) {
 #pragma unroll

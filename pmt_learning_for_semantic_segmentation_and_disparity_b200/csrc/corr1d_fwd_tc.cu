@@ -191,7 +191,7 @@ corr1d_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmL, const __grid_const
     // ===== epilogue warps: TMEM -> registers -> un-skewed staging tile -> TMA store =====
     const int q = wid & 3;               // TMEM lane quarter this warp may access
     const int wl = 32 * q + lane;        // output column within the tile (= TMEM lane)
-    int it = 0, gstep = 0;
+    int it = 0, sbuf = 0;   // staging buffer of the current step (a running index: `gstep % n_bufs` was 10% of the kernel's instructions)
     for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x, ++it) {
       const int wt = tile % a.n_wtiles, h = (tile / a.n_wtiles) % a.H, n = tile / (a.n_wtiles * a.H);
       mbar_wait(tmem_full, (uint32_t)it & 1u);
@@ -205,8 +205,8 @@ corr1d_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmL, const __grid_const
       float vp[32], vc[32];
       tc::tmem_ld32(tmem_base + ((uint32_t)(32 * q) << 16) + (uint32_t)(32 * q + a.delta), vp);
       const int r0 = (32 - lane) & 31;
-      for (int s = 0; s < a.n_steps; ++s, ++gstep) {
-        float* tile_s = reinterpret_cast<float*>(smem + a.tile_off + (gstep % a.n_bufs) * kStepBytes);
+      for (int s = 0; s < a.n_steps; ++s, sbuf = (sbuf + 1 == a.n_bufs) ? 0 : sbuf + 1) {
+        float* tile_s = reinterpret_cast<float*>(smem + a.tile_off + sbuf * kStepBytes);
         tc::tmem_ld32(tmem_base + ((uint32_t)(32 * q) << 16) + (uint32_t)(32 * (s + q + 1) + a.delta), vc);
         if (s == a.n_steps - 1) {
           tc::fence_before_sync();
@@ -446,7 +446,7 @@ corr1d_fwd_tca_kernel(const __grid_constant__ CUtensorMap tmL, const __grid_cons
     const int q = wid & 3;               // TMEM lane quarter this warp may access
     const int hsel = (wid - 2) >> 2;     // which half of every block
     const int wl = 32 * q + lane;        // output column within the tile (= TMEM lane)
-    int it = 0, gstep = 0;
+    int it = 0, sbuf = 0;   // staging buffer of the current step (a running index: `gstep % n_bufs` was 10% of the kernel's instructions)
     for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x, ++it) {
       const int wt = tile % a.n_wtiles, h = (tile / a.n_wtiles) % a.H, n = tile / (a.n_wtiles * a.H);
       mbar_wait(tmem_full, (uint32_t)it & 1u);
@@ -460,8 +460,8 @@ corr1d_fwd_tca_kernel(const __grid_constant__ CUtensorMap tmL, const __grid_cons
       tc::tmem_ld_wait16(vp);
       tc::tmem_ld_wait16(vc);
       const int r0 = (32 - lane + 16 * hsel) & 31;
-      for (int s = 0; s < a.n_steps; ++s, ++gstep) {
-        float* tile_s = reinterpret_cast<float*>(smem + a.tile_off + (gstep % a.n_bufs) * kStepBytes);
+      for (int s = 0; s < a.n_steps; ++s, sbuf = (sbuf + 1 == a.n_bufs) ? 0 : sbuf + 1) {
+        float* tile_s = reinterpret_cast<float*>(smem + a.tile_off + sbuf * kStepBytes);
         if (s + 1 < a.n_steps) {
           tc::tmem_ld16_async(tcol + (uint32_t)(32 * (s + q + 2)), vn);
         } else {
