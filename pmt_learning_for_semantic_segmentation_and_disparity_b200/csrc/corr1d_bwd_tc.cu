@@ -317,6 +317,7 @@ corr1d_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmIn1, const __grid_con
           const uint64_t dB = dB0 + (uint64_t)(b_step * (uint32_t)bs);
           const uint32_t ta = tmem_base + (uint32_t)(a.a_base + gs * a.aslot_cols);
           const uint64_t dA = dA0 + (uint64_t)(a_step * (uint32_t)gs);
+          PSEC_BEGIN();
           if (tc::elect_one()) {
             if (!skip) {
               if (tmem_a) {
@@ -345,11 +346,13 @@ corr1d_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmIn1, const __grid_con
                 }
               }
             }
+            PSEC_END(0);   // profiling build: cycles in the MMA issue (the thread blocks while the tensor queue is full)
             tc::mma_commit(&gd_empty[gs]);
             tc::mma_commit(&band_empty[bs]);
             if (k == a.NKC - 1) tc::mma_commit(&tmem_full[buf]);
           }
           __syncwarp();
+          PSEC_END(1);     // issue + commits + reconvergence
           if (++gs == m.a_slots) gs = 0, gph ^= 1u;
           if (++bs == m.band_slots) bs = 0, bph ^= 1u;
         }
