@@ -6,7 +6,7 @@ N=$(nvidia-smi -L | wc -l)
 L=gpurun_out/r2_call29_n$N.log
 {
 echo "gpus=$N"
-timeout 420 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29547 bench.py --gpus $N --steps 20 --warmup 5 > gpurun_out/r2_bench_n$N.json 2> gpurun_out/r2_bench_n$N.err; echo "bench rc=$?"
+timeout 100 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29547 bench.py --gpus $N --steps 20 --warmup 5 > gpurun_out/r2_bench_n$N.json 2> gpurun_out/r2_bench_n$N.err; echo "bench rc=$?"
 tail -2 gpurun_out/r2_bench_n$N.err | cut -c1-300
 python - <<P
 import json
