@@ -460,10 +460,13 @@ corr1d_fwd_tca_kernel(const __grid_constant__ CUtensorMap tmL, const __grid_cons
       tc::tmem_ld_wait16(vp);
       tc::tmem_ld_wait16(vc);
       const int r0 = (32 - lane + 16 * hsel) & 31;
-      for (int s = 0; s < a.n_steps; ++s, sbuf = (sbuf + 1 == a.n_bufs) ? 0 : sbuf + 1) {
+      // One step: P = block s+q, C = block s+q+1, N = block s+q+2 (requested here).  The three register sets change roles
+      // from step to step by NAME (the loop below is unrolled by three), not by copying 32 registers per step.
+      auto step = [&](int s, uint32_t (&P)[16], uint32_t (&C)[16], uint32_t (&N)[16]) {
         float* tile_s = reinterpret_cast<float*>(smem + a.tile_off + sbuf * kStepBytes);
+        sbuf = (sbuf + 1 == a.n_bufs) ? 0 : sbuf + 1;
         if (s + 1 < a.n_steps) {
-          tc::tmem_ld16_async(tcol + (uint32_t)(32 * (s + q + 2)), vn);
+          tc::tmem_ld16_async(tcol + (uint32_t)(32 * (s + q + 2)), N);
         } else {
           tc::fence_before_sync();
           __syncwarp();
@@ -478,7 +481,7 @@ corr1d_fwd_tca_kernel(const __grid_constant__ CUtensorMap tmL, const __grid_cons
 #pragma unroll
         for (int j = 0; j < 16; ++j) {
           const int jj = 16 * hsel + j;
-          const uint32_t v = (jj >= lane) ? vp[j] : vc[j];
+          const uint32_t v = (jj >= lane) ? P[j] : C[j];
           col[((r0 + j) & 31) * kTM] = __uint_as_float(v);   // staging row = plane - 32s = (jj - lane) mod 32
         }
         fence_proxy_async();                       // generic-proxy writes -> visible to the TMA store
@@ -487,11 +490,15 @@ corr1d_fwd_tca_kernel(const __grid_constant__ CUtensorMap tmL, const __grid_cons
           tc::tma_store_4d(&tmO, tile_s, wt * kTM, h, kRowsPerStep * s, n);
           tc::tma_store_commit();
         }
-        if (s + 1 < a.n_steps) {
-          tc::tmem_ld_wait16(vn);                  // vn has landed (its latency overlapped the stores above)
-#pragma unroll
-          for (int j = 0; j < 16; ++j) vp[j] = vc[j], vc[j] = vn[j];
-        }
+        if (s + 1 < a.n_steps) tc::tmem_ld_wait16(N);   // N has landed (its latency overlapped the stores above)
+      };
+      for (int s = 0;;) {
+        step(s, vp, vc, vn);
+        if (++s >= a.n_steps) break;
+        step(s, vc, vn, vp);
+        if (++s >= a.n_steps) break;
+        step(s, vn, vp, vc);
+        if (++s >= a.n_steps) break;
       }
     }
     if (wid == 2 && lane == 0) tc::tma_store_wait<0>();
