@@ -38,21 +38,21 @@ constexpr int kGdBytes = kTM * kKC * 4;   // 16 KB: one A-operand chunk
 constexpr int kEpiWarps = 4;
 // Builder warps.  Every builder warp pays a fixed cost per chunk (barrier waits, tcgen05.st / fences, arrive, ring
 // bookkeeping) on top of the elements it moves, so few, fat warps win over many thin ones (16 -> 8 warps: 366 -> 341 us
-// at the headline shape, issue-slot utilisation 64% -> 47%).  The builders work in groups of 4 warps (one per TMEM lane
-// quarter) that take chunks round-robin, so a group's latency chain (waits, build, fence, arrive) overlaps the other
-// groups'.  Every ring a group waits on needs one slot per group (parity waits tolerate one phase of lead per waiter),
-// so 3 groups are used when 3 shared-memory A-operand slots fit for gin2 (C <= 64: 345 -> 333 us), else 2.
+// at the headline shape).  The builders work in groups of 4 warps (one per TMEM lane quarter) that take chunks
+// round-robin, so a group's latency chain (waits, build, fence, arrive) overlaps the other groups'.  Every ring a group
+// waits on needs one slot per group (parity waits tolerate one phase of lead per waiter).  3 groups are used when the
+// rings fit (both A operands in TMEM, or three shared-memory A slots for gin2 at C <= 64), else 2.
 template <int kPasses, int kGroups_>
 struct BwdCfg {
   static constexpr int kGroups = kGroups_;
   static constexpr int kGroupWarps = 4;
   static constexpr int kBuilders = kGroupWarps * kGroups;
-  // 3xTF32: two more warps split the landed feature band into hi / lo (they take the K chunks alternately).  The
-  // builders used to do it at the end of every chunk; a cycle-stamped profile of one CTA showed a builder group spending
-  // ~900 of its ~3800 cycles per chunk there (a barrier wait, 8 KB through LDS/STS, a proxy fence), and the rate of the
-  // kernel is kGroups chunks per such group cycle.  21 warps x 96 registers still fit the register file.
-  // Two teams take the chunks alternately (a ring a team waits on needs one slot per team: band_slots >= 2); with 2
-  // builder groups (wide bands: C = 128 is 16 KB per chunk) a team is two warps that split a chunk between them.
+  // 3xTF32: dedicated warps split the landed feature band into hi / lo.  The builders used to do it at the end of every
+  // chunk; a cycle-stamped profile of one CTA showed a builder group spending ~900 of its ~3800 cycles per chunk there (a
+  // barrier wait, 8 KB through LDS/STS, a proxy fence), and the rate of the kernel is kGroups chunks per such group cycle.
+  // Two teams take the chunks alternately (a ring a team waits on needs one slot per team: band_slots >= 2, and a team must
+  // never start on the ring's second phase -- a parity test on a fresh barrier passes at once); a team is 2 warps that
+  // share a chunk (4 with 2 builder groups: wide bands, C = 128 is 16 KB per chunk).  23 warps x 80 registers fit.
   static constexpr int kSplitTeams = 2;
   static constexpr int kSplitPer = kGroups_ == 2 ? 4 : 2;
   static constexpr int kSplitWarps = kPasses == 3 ? kSplitTeams * kSplitPer : 0;
