@@ -208,7 +208,7 @@ def child_group_env(rank: int, local_rank: int, world_size: int, port_offset: in
     return env
 
 
-def run_step_record(world, timeout_s: float = 300.0):
+def run_step_record(world, timeout_s: float = 150.0):
     """Data-parallel training step (north_star: "1 GPU and 2/4/8 GPUs for the data-parallel training step"): every rank
     spawns bench_step.py as a child process that joins its OWN process group on MASTER_PORT+1, so a problem there
     (NCCL graph capture, teardown) can never take the headline measurement down with it.  Rank 0 returns the child's
